@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — batched iLQR iterations/sec (acrobot, T=200) on N B200s, next to the CPU reference.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--config cfg2|cfg4|cfg5]
+
+One STEP = one pass of the hot path over one batch of synthetic instances (SURVEY.md §8d,
+include/ilqr_synth.h, seed 12345): every instance is initialised (`iLQR::init_traj`) and solved to
+termination (`iLQR::generate_trajectory`) — derivative sweeps, backward passes with boxQP, line
+searches, lambda schedule.  The metric counts the loop trips of src/ilqr_core.cpp:103-288 actually
+executed, summed over the batch, per second.
+
+  value  inputs already resident in HBM; timed with CUDA events on the library's stream.
+  e2e    the same through the C ABI with HOST buffers: pinned x0/u0 -> H2D -> solve -> D2H of the
+         final costs and trip counts, copies inside the timed region.
+  roofline  the solve kernel alone: ALGORITHMIC bytes (40 096 B per accepted and
+         32 064 B per rejected trip at n=4, m=1, T=200, f64) / its CUDA-event duration, against the
+         measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/libref_oracle.so, built from /root/reference
+         by oracle/Makefile) on the host cores, one forked worker per core, on a bounded sample of
+         the same batch.
+
+N > 1 (torchrun, one rank per GPU): every rank solves its own B instances (weak scaling, no
+data-path collective) and the final costs are gathered to rank 0 with ONE NCCL gather per step.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "batched iLQR iterations/sec (acrobot T=200)"
+UNIT = "iterations/s"
+SEED = 12345
+
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "cfg2": dict(workload="acrobot batch=4096 T=200 fp64, analytic cost derivatives, FD fx/fu (BASELINE configs[1])",
+                 B=4096, T=200, cost_deriv="analytic", limits=None),
+    # configs[3]: control-limited, full finite differences
+    "cfg4": dict(workload="control-limited acrobot (+-1.5) batch=8192 T=200 fp64, full finite differences (BASELINE configs[3])",
+                 B=8192, T=200, cost_deriv="fd", limits=1.5),
+    # configs[4] per-GPU shard: 1 048 576 / 8
+    "cfg5": dict(workload="acrobot batch=131072 per GPU T=200 fp64, analytic cost derivatives (BASELINE configs[4] shard)",
+                 B=131072, T=200, cost_deriv="analytic", limits=None),
+}
+
+
+def bytes_per_trip(n, m, T, s):
+    """algorithmic HBM bytes of one accepted / rejected loop trip of one trajectory."""
+    acc = s * (3 * ((T + 1) * n + T * m) + 2 * T * m * (n + 1))
+    rej = s * (2 * ((T + 1) * n + T * m) + 2 * T * m * (n + 1))
+    return acc, rej
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, b0, b1, x0, u0, T, limits, cost_deriv = args
+    if kind == "reference":
+        import refharness as R
+        L = R.lib()
+        L.ref_solve_range.restype = C.c_long
+        L.ref_solve_range.argtypes = [C.c_void_p, C.c_long, C.c_long, R._dp, R._dp, C.c_int, C.c_int, R._dp, R._ip, R._ip]
+        lo = [-limits] if limits else None
+        hi = [limits] if limits else None
+        s = R.RefSolver(R.ACROBOT, 0.02, u_min=lo, u_max=hi)
+        cost = np.empty(b1 - b0)
+        iters = np.zeros(b1 - b0, dtype=np.int32)
+        status = np.zeros(b1 - b0, dtype=np.int32)
+        t0 = time.perf_counter()
+        total = L.ref_solve_range(s.h, b0, b1, R._p(x0), R._p(u0), T, -1, R._p(cost), iters.ctypes.data_as(R._ip),
+                                  status.ctypes.data_as(R._ip))
+        return total, time.perf_counter() - t0, cost
+    import oracleport as O
+    from ilqr_b200 import abi
+    kw = dict(u_min=[-limits], u_max=[limits]) if limits else {}
+    desc = abi.make_desc(model=abi.MODEL_ACROBOT, T=T, dt=0.02,
+                         cost_deriv=abi.COST_ANALYTIC if cost_deriv == "analytic" else abi.COST_FD, **kw)
+    t0 = time.perf_counter()
+    r = O.solve_range(desc, x0, u0, b0, b1)
+    return int(r["total_trips"]), time.perf_counter() - t0, r["cost"]
+
+
+def cpu_reference_kind():
+    import refharness as R
+    return "reference" if R.available() else "port"
+
+
+def run_cpu_sample(cfg, x0, u0, n_sample, cores):
+    """Solve instances [0, n_sample) with the reference on `cores` forked workers; returns
+    (iterations, wall seconds, costs)."""
+    kind = cpu_reference_kind()
+    n_sample = min(n_sample, x0.shape[0])
+    x0 = np.ascontiguousarray(x0[:n_sample])
+    u0 = np.ascontiguousarray(u0[:n_sample])
+    cores = max(1, min(cores, n_sample))
+    bounds = np.linspace(0, n_sample, cores + 1).astype(int)
+    jobs = [(kind, int(bounds[i]), int(bounds[i + 1]), x0, u0, cfg["T"], cfg["limits"], cfg["cost_deriv"])
+            for i in range(cores) if bounds[i + 1] > bounds[i]]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(jobs)) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    iters = sum(r[0] for r in res)
+    cost = np.concatenate([r[2] for r in res])
+    return kind, iters, wall, cost, len(jobs)
+
+
+def synth_inputs(B, T, seed):
+    """include/ilqr_synth.h through the library's own generator when it is built, else numpy-free C port."""
+    from ilqr_b200.solver import make_inputs
+    return make_inputs(seed, B, T, 4, 1)
+
+
+def synth_inputs_cpu(B, T, seed):
+    """Same generator without loading the CUDA library (the reference arm must not touch our engine)."""
+    src = os.path.join(ROOT, "tests", "_build", "libsynth.so")
+    if not os.path.exists(src):
+        os.makedirs(os.path.dirname(src), exist_ok=True)
+        csrc = os.path.join(ROOT, "tests", "_build", "synth.c")
+        with open(csrc, "w") as f:
+            f.write('#include "ilqr_synth.h"\nvoid synth(unsigned long long seed, long B, int T, int n, int m, double xs, double us, int c, double *x0, double *u0) { ilqr_synth_fill(seed, (size_t)B, T, n, m, xs, us, c, x0, u0); }\n')
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-o", src, csrc])
+    L = C.CDLL(src)
+    dp = C.POINTER(C.c_double)
+    L.synth.argtypes = [C.c_ulonglong, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, dp, dp]
+    x0 = np.empty((B, 4))
+    u0 = np.empty((B, T, 1))
+    L.synth(seed, B, T, 4, 1, 1.0, 0.5, 1, x0.ctypes.data_as(dp), u0.ctypes.data_as(dp))
+    return x0, u0
+
+
+def reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = args.batch or cfg["B"]
+    per_core = args.cpu_per_core
+    n_sample = min(B, cores * per_core)
+    x0, u0 = synth_inputs_cpu(n_sample, cfg["T"], SEED)
+    times, iters = [], []
+    kind = cpu_reference_kind()
+    for step in range(args.warmup + args.steps):
+        kind, it, wall, _, used = run_cpu_sample(cfg, x0, u0, n_sample, cores)
+        if step >= args.warmup:
+            times.append(wall)
+            iters.append(it)
+    total_t = sum(times)
+    value = sum(iters) / total_t
+    sample = "first %d of %d instances per step, solved to termination, %d forked workers" % (n_sample, B, used)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "sample": sample, "timer": "host wall clock (CPU arm)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+                power.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from ilqr_b200 import abi
+    from ilqr_b200.solver import BatchILQR
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the solver has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.batch or cfg["B"], cfg["T"]
+    n, m = 4, 1
+    cd = abi.COST_ANALYTIC if cfg["cost_deriv"] == "analytic" else abi.COST_FD
+    kw = dict(u_min=[-cfg["limits"]], u_max=[cfg["limits"]]) if cfg["limits"] else {}
+    x0, u0 = synth_inputs(B, T, SEED + rank)  # every rank owns different instances
+    solver = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cd, device=local, **kw)
+    stream = torch.cuda.ExternalStream(solver.stream, device=dev)
+
+    x0_h = torch.from_numpy(x0).pin_memory()
+    u0_h = torch.from_numpy(u0).pin_memory()
+    cost_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    iters_h = torch.empty(B, dtype=torch.int32).pin_memory()
+    x0_d, u0_d = x0_h.to(dev), u0_h.to(dev)
+    cost_d = torch.empty(B, dtype=torch.float64, device=dev)
+    gathered = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def gather_costs():
+        if world > 1:
+            dist.gather(cost_d, gathered, dst=0)
+
+    def step_resident():
+        """inputs resident in HBM -> final costs resident in HBM (rank 0 after the gather)"""
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        with torch.cuda.stream(stream):
+            e0.record()
+            solver.set_initial_device(x0_d.data_ptr(), u0_d.data_ptr())
+            e1.record()
+            solver.solve()
+            e2.record()
+            solver.get_device("cost", cost_d.data_ptr())
+            gather_costs()
+            e3.record()
+        return e0, e1, e2, e3
+
+    def step_e2e():
+        """host buffers in, host results out, through the C ABI"""
+        e0, e3 = ev(), ev()
+        with torch.cuda.stream(stream):
+            e0.record()
+            solver.set_initial(x0_h.numpy(), u0_h.numpy())
+            solver.solve()
+            solver.get("cost", out=cost_h.numpy())
+            solver.get("iters", out=iters_h.numpy())
+            if world > 1:
+                cost_d.copy_(cost_h, non_blocking=True)
+                gather_costs()
+            e3.record()
+        return e0, e3
+
+    def do_flush():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = solver.launch_count
+    # ---- timed region 1: resident inputs ------------------------------------------------------
+    barrier()
+    wall0 = time.perf_counter()
+    evs, trips, acc, rej = [], 0, 0, 0
+    for _ in range(args.steps):
+        do_flush()
+        evs.append(step_resident())
+        solver.sync()
+        trips += int(solver.get("iters").sum())
+        acc += int(solver.get("n_accept").sum())
+        rej += int(solver.get("n_reject").sum())
+    barrier()
+    wall_resident = time.perf_counter() - wall0
+    launches = solver.launch_count - launches0
+    step_ms = [e[0].elapsed_time(e[3]) for e in evs]
+    solve_ms = [e[1].elapsed_time(e[2]) for e in evs]
+    # ---- timed region 2: end to end ---------------------------------------------------------------
+    barrier()
+    evs2 = []
+    trips_e2e = 0
+    for _ in range(args.steps):
+        do_flush()
+        evs2.append(step_e2e())
+        torch.cuda.synchronize()
+        trips_e2e += int(iters_h.sum())
+    barrier()
+    e2e_ms = [e[0].elapsed_time(e[1]) for e in evs2]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # whole-job numbers: sum of trips over ranks / max time over ranks
+    t_res = torch.tensor([sum(step_ms), sum(e2e_ms), sum(solve_ms)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([trips, trips_e2e, acc, rej], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t_res, cnt = t_res.tolist(), cnt.tolist()
+    if rank == 0:
+        value = cnt[0] / (t_res[0] * 1e-3)
+        e2e = cnt[1] / (t_res[1] * 1e-3)
+        b_acc, b_rej = bytes_per_trip(n, m, T, 8)
+        alg_bytes_per_launch = (cnt[2] * b_acc + cnt[3] * b_rej) / world / args.steps  # per GPU per solve launch
+        solve_s = t_res[2] * 1e-3 / args.steps
+        achieved = alg_bytes_per_launch / solve_s / 1e9
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_res[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "batch_per_gpu": B, "T": T, "seed": SEED,
+                       "step": "init_traj + generate_trajectory to termination for every instance; one NCCL gather of final costs when N>1",
+                       "l2": "512 MiB buffer written between timed steps (L2 flush)",
+                       "trips_per_step": cnt[0] / args.steps, "accepted": cnt[2] / args.steps, "rejected": cnt[3] / args.steps,
+                       "wall_s_resident_region": wall_resident},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": t_res[1] / args.steps,
+                    "h2d_bytes_per_step": int(world * (x0_h.numel() + u0_h.numel()) * 8),
+                    "d2h_bytes_per_step": int(world * (B * 8 + B * 4))},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "ilqr_warp_kernel<Acrobot,double,%s> (op_iterate)" % cfg["cost_deriv"],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": solve_s * 1e3,
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                         "note": "fp64 finite-difference + boxQP arithmetic bounds this kernel (SURVEY.md §8d secondary ceiling), not HBM"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_sample = min(B, cores * args.cpu_per_core)
+            kind, it, wall, cpu_cost, used = run_cpu_sample(cfg, x0, u0, n_sample, cores)
+            gcost = cost_h.numpy()[:n_sample]
+            rel = np.abs(gcost - cpu_cost) / np.maximum(np.abs(cpu_cost), 1e-300)
+            line["cpu_baseline"] = {"value": it / wall, "unit": UNIT, "cores": used, "kind": kind,
+                                    "sample": "first %d of %d instances, solved to termination, %d forked workers, %.1f s wall"
+                                              % (n_sample, B, used, wall),
+                                    "max_rel_cost_diff_vs_gpu": float(rel.max())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override instances per GPU")
+    ap.add_argument("--cpu-per-core", type=int, default=48, help="CPU baseline: instances per host core in the sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        reference_arm(args, cfg)
+    else:
+        ours_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

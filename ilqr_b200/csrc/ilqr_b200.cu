@@ -1,0 +1,406 @@
+/*
+ * ilqr_b200.cu — kernels and the extern "C" ABI (include/ilqr_b200.h) of libilqr_b200.so.
+ *
+ * One persistent warp per trajectory: every warp of the grid pulls problem instances from an
+ * atomic queue and runs the whole operation for that instance (ilqr_core.cuh) with its working
+ * set in its private slice of shared memory; warps never synchronise with each other.  The grid
+ * is sized to fill the 148 SMs at the kernel's occupancy, so ragged per-trajectory iteration
+ * counts are absorbed by the queue.  One launch per ABI call (`ilqr_solve` = one launch).
+ *
+ * HBM layout (per handle, scalar type S = f64 or f32), trajectory-major and contiguous in t so a
+ * warp streams its own trajectory with coalesced tile copies; identical to the host layout of
+ * the ABI, so set/get are plain copies:
+ *     x0 [B][n]   xs [B][T+1][n]   us [B][T][m]   K [B][T][m][n]   k [B][T][m]
+ *     Vx0 [B][n]  Vxx0 [B][n][n]   st [B] (TrajState: cost, lambda, dlambda, dV, counters ...)
+ *
+ * There is no CPU path in this library: every entry point that computes launches a kernel.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/ilqr_b200.h"
+#include "../../include/ilqr_synth.h"
+#include "ilqr_core.cuh"
+#include "params.h"
+
+using namespace ilqr;
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+enum Op { kOpInit = 0, kOpWarm = 1, kOpIterate = 2, kOpBackwardOnce = 3, kOpRolloutOnce = 4 };
+
+template <typename S>
+struct KArgs {
+  SolveParams<S> P;
+  const S *x0;
+  S *xs, *us, *K, *k, *Vx0, *Vxx0;
+  TrajState<S> *st;
+  unsigned long long *queue;
+  long long B;
+  int op;
+  int n_iters;
+  S scalar; /* lambda (backward_once) or alpha (rollout_once) */
+};
+
+template <class Model, typename S, int CD>
+__global__ void __launch_bounds__(kThreads) ilqr_warp_kernel(const __grid_constant__ KArgs<S> a) {
+  constexpr int N = Model::N, M = Model::M;
+  using Sc = Scratch<N, M, S>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Sc &sc = reinterpret_cast<Sc *>(smem_raw)[threadIdx.x >> 5];
+  WarpExec<N, S> ex;
+  ex.lane = threadIdx.x & 31;
+  const int T = a.P.T;
+  for (;;) {
+    unsigned long long b = 0;
+    if (ex.lane == 0) b = atomicAdd(a.queue, 1ULL);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if ((long long)b >= a.B) break;
+    TrajPtrs<S> tr;
+    tr.x0 = a.x0 + b * N;
+    tr.xs = a.xs + b * (size_t)(T + 1) * N;
+    tr.us = a.us + b * (size_t)T * M;
+    tr.K = a.K + b * (size_t)T * M * N;
+    tr.k = a.k + b * (size_t)T * M;
+    tr.Vx0 = a.Vx0 + b * N;
+    tr.Vxx0 = a.Vxx0 + b * N * N;
+    tr.st = a.st + b;
+    Core<Model, S, CD, WarpExec<N, S>> core(a.P, sc, ex, tr);
+    switch (a.op) {
+      case kOpInit: core.op_init(); break;
+      case kOpWarm: core.op_warm_start(); break;
+      case kOpIterate: core.op_iterate(a.n_iters); break;
+      case kOpBackwardOnce: core.op_backward_once(a.scalar); break;
+      case kOpRolloutOnce: core.op_rollout_once(a.scalar); break;
+      default: break;
+    }
+    __syncwarp();
+  }
+}
+
+/* per-trajectory scalars out of the state records, one thread per trajectory */
+template <typename S>
+__global__ void ilqr_gather_kernel(const TrajState<S> *st, long long B, int field, void *out) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const TrajState<S> &s = st[b];
+  S *fo = (S *)out;
+  int32_t *io = (int32_t *)out;
+  switch (field) {
+    case ILQR_F_COST: fo[b] = s.cost; break;
+    case ILQR_F_DV: fo[2 * b] = s.dV0; fo[2 * b + 1] = s.dV1; break;
+    case ILQR_F_LAMBDA: fo[b] = s.lam; break;
+    case ILQR_F_DLAMBDA: fo[b] = s.dlam; break;
+    case ILQR_F_GNORM: fo[b] = s.gnorm; break;
+    case ILQR_F_ITERS: io[b] = s.trips; break;
+    case ILQR_F_STATUS: io[b] = s.status; break;
+    case ILQR_F_ALPHA_INDEX: io[b] = s.alpha_index; break;
+    case ILQR_F_N_ACCEPT: io[b] = s.n_accept; break;
+    case ILQR_F_N_REJECT: io[b] = s.n_reject; break;
+    case ILQR_F_N_BACKWARD: io[b] = s.n_backward; break;
+    case ILQR_F_DIVERGE: io[b] = s.diverge; break;
+    default: break;
+  }
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct ilqr_handle {
+  ilqr_desc desc;
+  int n = 0, m = 0;
+  size_t ssize = 8;
+  cudaStream_t stream = nullptr;
+  void *x0 = nullptr, *xs = nullptr, *us = nullptr, *K = nullptr, *k = nullptr, *Vx0 = nullptr, *Vxx0 = nullptr,
+       *st = nullptr, *tmp = nullptr;
+  unsigned long long *queue = nullptr;
+  int num_sms = 0;
+  int64_t launches = 0;
+  bool initialised = false;
+  std::string err;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int fail(ilqr_handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+#define CU(h, call)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(h, ILQR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+  } while (0)
+
+template <class Model, typename S, int CD>
+int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
+  constexpr int N = Model::N, M = Model::M;
+  KArgs<S> a;
+  if (make_solve_params<S>(h->desc, &a.P) != 0) return fail(h, ILQR_E_INVALID, "bad parameters");
+  a.x0 = (const S *)h->x0;
+  a.xs = (S *)h->xs;
+  a.us = (S *)h->us;
+  a.K = (S *)h->K;
+  a.k = (S *)h->k;
+  a.Vx0 = (S *)h->Vx0;
+  a.Vxx0 = (S *)h->Vxx0;
+  a.st = (TrajState<S> *)h->st;
+  a.queue = h->queue;
+  a.B = h->desc.B;
+  a.op = op;
+  a.n_iters = n_iters;
+  a.scalar = S(scalar);
+  auto kern = ilqr_warp_kernel<Model, S, CD>;
+  const size_t smem = sizeof(Scratch<N, M, S>) * kWarpsPerCta;
+  if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) return fail(h, ILQR_E_CUDA, "kernel does not fit on an SM");
+  long long want = (h->desc.B + kWarpsPerCta - 1) / kWarpsPerCta;
+  long long cap = (long long)per_sm * h->num_sms;
+  const int grid = (int)(want < cap ? want : cap);
+  CU(h, cudaMemsetAsync(h->queue, 0, sizeof(unsigned long long), h->stream));
+  kern<<<grid, kThreads, smem, h->stream>>>(a);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return ILQR_OK;
+}
+
+template <class Model, typename S>
+int launch_cd(ilqr_handle *h, int op, int n_iters, double scalar) {
+  if (h->desc.cost_deriv == ILQR_COST_ANALYTIC) return launch_t<Model, S, kCostAnalytic>(h, op, n_iters, scalar);
+  return launch_t<Model, S, kCostFD>(h, op, n_iters, scalar);
+}
+template <class Model>
+int launch_s(ilqr_handle *h, int op, int n_iters, double scalar) {
+  if (h->desc.dtype == ILQR_F32) return launch_cd<Model, float>(h, op, n_iters, scalar);
+  return launch_cd<Model, double>(h, op, n_iters, scalar);
+}
+int launch(ilqr_handle *h, int op, int n_iters, double scalar) {
+  if (h->desc.model_id == ILQR_MODEL_ACROBOT) return launch_s<Acrobot>(h, op, n_iters, scalar);
+  return launch_s<DoubleIntegrator>(h, op, n_iters, scalar);
+}
+
+size_t state_size(const ilqr_handle *h) {
+  return h->desc.dtype == ILQR_F32 ? sizeof(TrajState<float>) : sizeof(TrajState<double>);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ilqr_default_params(ilqr_params *p) {
+  if (!p) return ILQR_E_INVALID;
+  default_params(p);
+  return ILQR_OK;
+}
+
+int ilqr_model_info(int32_t model_id, int32_t *n, int32_t *m, double *u_min, double *u_max) {
+  int nn, mm;
+  if (model_info(model_id, &nn, &mm, u_min, u_max) != 0) return ILQR_E_INVALID;
+  if (n) *n = nn;
+  if (m) *m = mm;
+  return ILQR_OK;
+}
+
+const char *ilqr_last_error(const ilqr_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ilqr_destroy(ilqr_handle *h) {
+  if (!h) return ILQR_OK;
+  {
+    DeviceGuard g(h->desc.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *bufs[] = {h->x0, h->xs, h->us, h->K, h->k, h->Vx0, h->Vxx0, h->st, h->tmp, h->queue};
+    for (void *b : bufs)
+      if (b) cudaFree(b);
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+  return ILQR_OK;
+}
+
+int ilqr_create(const ilqr_desc *desc, ilqr_handle **out) {
+  if (!desc || !out) return fail(nullptr, ILQR_E_INVALID, "null argument");
+  *out = nullptr;
+  int n, m;
+  if (model_info(desc->model_id, &n, &m, nullptr, nullptr) != 0) return fail(nullptr, ILQR_E_INVALID, "unknown model_id");
+  if (desc->dtype != ILQR_F64 && desc->dtype != ILQR_F32) return fail(nullptr, ILQR_E_INVALID, "unknown dtype");
+  if (desc->cost_deriv != ILQR_COST_FD && desc->cost_deriv != ILQR_COST_ANALYTIC)
+    return fail(nullptr, ILQR_E_INVALID, "unknown cost_deriv");
+  if (desc->B < 1 || desc->T < 1) return fail(nullptr, ILQR_E_INVALID, "B and T must be positive");
+  if (!(desc->dt > 0)) return fail(nullptr, ILQR_E_INVALID, "dt must be positive");
+  {
+    SolveParams<double> chk;
+    if (make_solve_params<double>(*desc, &chk) != 0) return fail(nullptr, ILQR_E_INVALID, "bad solver parameters");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(nullptr, ILQR_E_CUDA, "no CUDA device: this library has no CPU path");
+  if (desc->device < 0 || desc->device >= ndev) return fail(nullptr, ILQR_E_INVALID, "device ordinal out of range");
+  ilqr_handle *h = new (std::nothrow) ilqr_handle;
+  if (!h) return fail(nullptr, ILQR_E_NOMEM, "out of host memory");
+  h->desc = *desc;
+  h->n = n;
+  h->m = m;
+  h->ssize = desc->dtype == ILQR_F32 ? 4 : 8;
+  DeviceGuard g(desc->device);
+  const size_t B = (size_t)desc->B, T = (size_t)desc->T, s = h->ssize;
+  struct {
+    void **p;
+    size_t bytes;
+  } allocs[] = {{&h->x0, B * n * s},          {&h->xs, B * (T + 1) * n * s}, {&h->us, B * T * m * s},
+                {&h->K, B * T * m * n * s},   {&h->k, B * T * m * s},        {&h->Vx0, B * n * s},
+                {&h->Vxx0, B * n * n * s},    {&h->st, B * state_size(h)},   {&h->tmp, B * 2 * 8},
+                {(void **)&h->queue, sizeof(unsigned long long)}};
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  for (auto &al : allocs) {
+    if (e != cudaSuccess) break;
+    e = cudaMalloc(al.p, al.bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(*al.p, 0, al.bytes, h->stream);
+  }
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, desc->device);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    const int code = e == cudaErrorMemoryAllocation ? ILQR_E_NOMEM : ILQR_E_CUDA;
+    fail(nullptr, code, std::string("ilqr_create: ") + cudaGetErrorString(e));
+    ilqr_destroy(h);
+    return code;
+  }
+  *out = h;
+  return ILQR_OK;
+}
+
+int ilqr_set_initial(ilqr_handle *h, const void *x0, const void *u0, int on_device) {
+  if (!h || !x0 || !u0) return fail(h, ILQR_E_INVALID, "null argument");
+  DeviceGuard g(h->desc.device);
+  const size_t B = (size_t)h->desc.B, T = (size_t)h->desc.T, s = h->ssize;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CU(h, cudaMemcpyAsync(h->x0, x0, B * h->n * s, kind, h->stream));
+  CU(h, cudaMemcpyAsync(h->us, u0, B * T * h->m * s, kind, h->stream));
+  CU(h, cudaMemsetAsync(h->K, 0, B * T * h->m * h->n * s, h->stream)); /* src/ilqr_core.cpp:44-48 */
+  CU(h, cudaMemsetAsync(h->k, 0, B * T * h->m * s, h->stream));
+  const int rc = launch(h, kOpInit, 0, 0.0);
+  if (rc == ILQR_OK) h->initialised = true;
+  return rc;
+}
+
+int ilqr_warm_start(ilqr_handle *h, const void *x0, int on_device) {
+  if (!h || !x0) return fail(h, ILQR_E_INVALID, "null argument");
+  if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_warm_start before ilqr_set_initial");
+  DeviceGuard g(h->desc.device);
+  CU(h, cudaMemcpyAsync(h->x0, x0, (size_t)h->desc.B * h->n * h->ssize,
+                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  return launch(h, kOpWarm, 0, 0.0);
+}
+
+int ilqr_iterate(ilqr_handle *h, int n_iters) {
+  if (!h) return ILQR_E_INVALID;
+  if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_iterate before ilqr_set_initial");
+  if (n_iters < 0) return fail(h, ILQR_E_INVALID, "n_iters must be >= 0");
+  DeviceGuard g(h->desc.device);
+  return launch(h, kOpIterate, n_iters, 0.0);
+}
+
+int ilqr_solve(ilqr_handle *h) {
+  if (!h) return ILQR_E_INVALID;
+  return ilqr_iterate(h, h->desc.params.max_iter + 1);
+}
+
+int ilqr_backward_once(ilqr_handle *h, double lambda) {
+  if (!h) return ILQR_E_INVALID;
+  if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_backward_once before ilqr_set_initial");
+  DeviceGuard g(h->desc.device);
+  return launch(h, kOpBackwardOnce, 0, lambda);
+}
+
+int ilqr_rollout_once(ilqr_handle *h, double alpha) {
+  if (!h) return ILQR_E_INVALID;
+  if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_rollout_once before ilqr_set_initial");
+  DeviceGuard g(h->desc.device);
+  return launch(h, kOpRolloutOnce, 0, alpha);
+}
+
+int ilqr_get(ilqr_handle *h, int field, void *dst, int on_device) {
+  if (!h || !dst) return fail(h, ILQR_E_INVALID, "null argument");
+  if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_get before ilqr_set_initial");
+  DeviceGuard g(h->desc.device);
+  const size_t B = (size_t)h->desc.B, T = (size_t)h->desc.T, s = h->ssize, n = h->n, m = h->m;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const void *src = nullptr;
+  size_t bytes = 0;
+  switch (field) {
+    case ILQR_F_XS: src = h->xs; bytes = B * (T + 1) * n * s; break;
+    case ILQR_F_US: src = h->us; bytes = B * T * m * s; break;
+    case ILQR_F_K: src = h->K; bytes = B * T * m * n * s; break;
+    case ILQR_F_KFF: src = h->k; bytes = B * T * m * s; break;
+    case ILQR_F_VX0: src = h->Vx0; bytes = B * n * s; break;
+    case ILQR_F_VXX0: src = h->Vxx0; bytes = B * n * n * s; break;
+    case ILQR_F_COST: case ILQR_F_LAMBDA: case ILQR_F_DLAMBDA: case ILQR_F_GNORM: bytes = B * s; break;
+    case ILQR_F_DV: bytes = B * 2 * s; break;
+    case ILQR_F_ITERS: case ILQR_F_STATUS: case ILQR_F_ALPHA_INDEX: case ILQR_F_N_ACCEPT: case ILQR_F_N_REJECT:
+    case ILQR_F_N_BACKWARD: case ILQR_F_DIVERGE: bytes = B * 4; break;
+    default: return fail(h, ILQR_E_INVALID, "unknown field");
+  }
+  if (!src) { /* a column of the state records: gather on the device, then one dense copy */
+    void *target = on_device ? dst : h->tmp;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((B + threads - 1) / threads);
+    if (h->desc.dtype == ILQR_F32)
+      ilqr_gather_kernel<float><<<blocks, threads, 0, h->stream>>>((const TrajState<float> *)h->st, (long long)B, field, target);
+    else
+      ilqr_gather_kernel<double><<<blocks, threads, 0, h->stream>>>((const TrajState<double> *)h->st, (long long)B, field, target);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    if (on_device) return ILQR_OK;
+    src = h->tmp;
+  }
+  CU(h, cudaMemcpyAsync(dst, src, bytes, kind, h->stream));
+  if (!on_device) CU(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int ilqr_sync(ilqr_handle *h) {
+  if (!h) return ILQR_E_INVALID;
+  DeviceGuard g(h->desc.device);
+  CU(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+void *ilqr_stream(ilqr_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int64_t ilqr_launch_count(const ilqr_handle *h) { return h ? h->launches : 0; }
+
+int ilqr_make_inputs(uint64_t seed, int64_t B, int32_t T, int32_t n, int32_t m, double x_scale, double u_scale,
+                     int canonical_first, double *x0, double *u0) {
+  if (B < 0 || T < 1 || n < 1 || m < 1 || !x0 || !u0) return ILQR_E_INVALID;
+  ilqr_synth_fill(seed, (size_t)B, T, n, m, x_scale, u_scale, canonical_first, x0, u0);
+  return ILQR_OK;
+}
+
+const char *ilqr_version(void) { return "ilqr_b200 0.1 sm_100a warp-per-trajectory f64/f32"; }
+
+}  // extern "C"

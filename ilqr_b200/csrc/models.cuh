@@ -1,0 +1,184 @@
+/*
+ * models.cuh — device twins of the reference's Model subclasses.
+ *
+ * The reference's plugin surface is a host vtable over dynamic Eigen vectors
+ * (include/model.h:6-21: dynamics / cost / final_cost, Euler integrate_dynamics :12-15).  Those
+ * headers cannot pass through nvcc (vendored Eigen 3.3.4 vs CUDA 12.9), so every model that runs
+ * on the GPU has a hand-written twin here: a struct with compile-time N (x_dims) and M (u_dims)
+ * and static functions over plain arrays, templated on the scalar type.
+ *
+ * Expressions are written in the order the reference evaluates them so that, built without FMA
+ * contraction, the f64 results are bit-identical to the reference model's up to the libm/libdevice
+ * difference in sin/cos.  Model parameters (`mp`) come from ilqr_desc::model_params.
+ */
+#ifndef ILQR_MODELS_CUH_
+#define ILQR_MODELS_CUH_
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define ILQR_HD __host__ __device__ __forceinline__
+#else
+#define ILQR_HD inline __attribute__((always_inline))
+#endif
+
+namespace ilqr {
+
+ILQR_HD double t_sin(double v) { return ::sin(v); }
+ILQR_HD double t_cos(double v) { return ::cos(v); }
+ILQR_HD double t_sqrt(double v) { return ::sqrt(v); }
+ILQR_HD double t_abs(double v) { return ::fabs(v); }
+ILQR_HD float t_sin(float v) { return ::sinf(v); }
+ILQR_HD float t_cos(float v) { return ::cosf(v); }
+ILQR_HD float t_sqrt(float v) { return ::sqrtf(v); }
+ILQR_HD float t_abs(float v) { return ::fabsf(v); }
+
+/* ------------------------------------------------------------------------------------------
+ * Acrobot — include/acrobot.h.  n = 4 (q1, q2, q1dot, q2dot), m = 1 (elbow torque) :27-28.
+ * mp[0..3] = goal, set to (3.1415, 0, 0, 0) by the library (the literal of :20-21, not pi).
+ * ---------------------------------------------------------------------------------------- */
+struct Acrobot {
+  static constexpr int N = 4;
+  static constexpr int M = 1;
+
+  /* Acrobot::dynamics :72-81 with H :43-51, C :53-61, G :63-70; parameters :19,23-25
+   * (I1 = I2 = l1 = l2 = m1 = m2 = 1, lc = 0.5, g = 9.81).  The 2x2 inverse is the closed form
+   * Eigen uses for fixed-size 2x2 (Eigen/src/LU/InverseImpl.h:76-94). */
+  template <typename S>
+  ILQR_HD static void dynamics(const S *x, const S *u, const S * /*mp*/, S *dx) {
+    const S I1 = 1, I2 = 1, l1 = 1, l2 = 1, m1 = 1, m2 = 1, g = S(9.81);
+    const S lc1 = S(0.5) * l1, lc2 = S(0.5) * l2;
+    const S q0 = x[0], q1 = x[1], qd0 = x[2], qd1 = x[3];
+    const S c2 = t_cos(q1);
+    const S H00 = I1 + I2 + m2 * l1 * l1 + 2 * m2 * l1 * lc2 * c2;
+    const S H01 = I2 + m2 * l1 * lc2 * c2;
+    const S H10 = I2 + m2 * l1 * lc2 * c2;
+    const S H11 = I2;
+    const S s2 = t_sin(q1);
+    const S C00 = -2 * m2 * l1 * lc2 * s2 * qd1;
+    const S C01 = -m2 * l2 * lc2 * s2 * qd1;
+    const S C10 = m2 * l1 * lc2 * s2 * qd0;
+    const S C11 = 0;
+    const S s1 = t_sin(q0);
+    const S s1p2 = t_sin(q0 + q1);
+    const S G0 = m1 * g * lc1 * s1 + m2 * g * (l1 * s1 + lc2 * s1p2);
+    const S G1 = m2 * g * lc2 * s1p2;
+    const S r0 = (S(0) - (C00 * qd0 + C01 * qd1)) - G0; /* Vector2d(0,u) - C*qdot - G */
+    const S r1 = (u[0] - (C10 * qd0 + C11 * qd1)) - G1;
+    const S det = H00 * H11 - H10 * H01;
+    const S invdet = S(1) / det;
+    const S Hi00 = H11 * invdet, Hi10 = -H10 * invdet, Hi01 = -H01 * invdet, Hi11 = H00 * invdet;
+    dx[0] = qd0;
+    dx[1] = qd1;
+    dx[2] = Hi00 * r0 + Hi01 * r1;
+    dx[3] = Hi10 * r0 + Hi11 * r1;
+  }
+  /* Acrobot::cost :83-92 — Ks = Kd = 0, Kr = 0.1 */
+  template <typename S>
+  ILQR_HD static S cost(const S *x, const S *u, const S *mp) {
+    const S e0 = mp[0] - x[0], e1 = mp[1] - x[1], e2 = mp[2] - x[2], e3 = mp[3] - x[3];
+    const S Ks = 0, Kd = 0, Kr = S(0.1);
+    return Ks * Ks * (e0 * e0 + e1 * e1) + Kd * Kd * (e2 * e2 + e3 * e3) + Kr * Kr * (u[0] * u[0]);
+  }
+  /* Acrobot::final_cost :94-100 — Ks = Kd = 20 */
+  template <typename S>
+  ILQR_HD static S final_cost(const S *x, const S *mp) {
+    const S e0 = mp[0] - x[0], e1 = mp[1] - x[1], e2 = mp[2] - x[2], e3 = mp[3] - x[3];
+    const S Ks = 20, Kd = 20;
+    return Ks * Ks * (e0 * e0 + e1 * e1) + Kd * Kd * (e2 * e2 + e3 * e3);
+  }
+  /* Closed-form cost derivatives (cost_deriv == ILQR_COST_ANALYTIC; the reference only has the
+   * finite-difference path).  All outputs are fully written. */
+  template <typename S>
+  ILQR_HD static void cost_derivs(const S *x, const S *u, const S *mp, bool terminal, S *cx, S *cu, S *cxx, S *cxu,
+                                  S *cuu) {
+#pragma unroll
+    for (int i = 0; i < N; i++) cx[i] = 0;
+#pragma unroll
+    for (int i = 0; i < N * N; i++) cxx[i] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) cxu[i] = 0;
+    cu[0] = 0;
+    if (terminal) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        cx[i] = S(-800.0) * (mp[i] - x[i]);
+        cxx[i * N + i] = S(800.0);
+      }
+    } else {
+      const S w = S(0.1) * S(0.1);
+      cu[0] = 2 * w * u[0];
+    }
+    cuu[0] = 2 * (S(0.1) * S(0.1));
+  }
+};
+
+/* ------------------------------------------------------------------------------------------
+ * DoubleIntegrator — include/double_integrator.h.  n = 4 (x, y, vx, vy), m = 2 (Fx, Fy) :16-17.
+ * mp[0..3] = goal (constructor argument :14).  Hx = diag(1, 1, .2, .2), Hu = I, mass 1 :19-24,51.
+ * ---------------------------------------------------------------------------------------- */
+struct DoubleIntegrator {
+  static constexpr int N = 4;
+  static constexpr int M = 2;
+
+  template <typename S>
+  ILQR_HD static void dynamics(const S *x, const S *u, const S * /*mp*/, S *dx) { /* :29-37 */
+    const S mass = 1;
+    dx[0] = x[2];
+    dx[1] = x[3];
+    dx[2] = u[0] / mass;
+    dx[3] = u[1] / mass;
+  }
+  template <typename S>
+  ILQR_HD static S quad(const S *x, const S *mp, S scale) {
+    const S hx[4] = {S(1), S(1), S(0.2), S(0.2)};
+    S acc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const S e = mp[i] - x[i];
+      acc += (e * (scale * hx[i])) * e;
+    }
+    return acc;
+  }
+  template <typename S>
+  ILQR_HD static S cost(const S *x, const S *u, const S *mp) { /* :39-43 */
+    return quad(x, mp, S(1)) + (u[0] * u[0] + u[1] * u[1]);
+  }
+  template <typename S>
+  ILQR_HD static S final_cost(const S *x, const S *mp) { /* :45-48 */
+    return quad(x, mp, S(10));
+  }
+  template <typename S>
+  ILQR_HD static void cost_derivs(const S *x, const S *u, const S *mp, bool terminal, S *cx, S *cu, S *cxx, S *cxu,
+                                  S *cuu) {
+    const S hx[4] = {S(1), S(1), S(0.2), S(0.2)};
+    const S sc = terminal ? S(10) : S(1);
+#pragma unroll
+    for (int i = 0; i < N * N; i++) cxx[i] = 0;
+#pragma unroll
+    for (int i = 0; i < N * M; i++) cxu[i] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      cx[i] = S(-2.0) * (sc * hx[i]) * (mp[i] - x[i]);
+      cxx[i * N + i] = S(2.0) * (sc * hx[i]);
+    }
+    cu[0] = terminal ? S(0) : 2 * u[0];
+    cu[1] = terminal ? S(0) : 2 * u[1];
+    cuu[0] = 2;
+    cuu[1] = 0;
+    cuu[2] = 0;
+    cuu[3] = 2;
+  }
+};
+
+/* Model::integrate_dynamics, include/model.h:12-15: x + dynamics(x, u) * dt */
+template <class Model, typename S>
+ILQR_HD void integrate(const S *x, const S *u, const S *mp, S dt, S *x1) {
+  S dx[Model::N];
+  Model::dynamics(x, u, mp, dx);
+#pragma unroll
+  for (int i = 0; i < Model::N; i++) x1[i] = x[i] + dx[i] * dt;
+}
+
+}  // namespace ilqr
+#endif

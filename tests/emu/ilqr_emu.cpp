@@ -1,0 +1,225 @@
+// tests/emu/ilqr_emu.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Compiles the kernel core (ilqr_b200/csrc/ilqr_core.cuh, the exact header the CUDA kernels
+// instantiate) with g++ and runs its warp phases lane by lane on the CPU (ilqr::HostExec), one
+// trajectory at a time.  Built with -ffp-contract=off, so for f64 the result must be
+// bit-identical to the oracle (oracle/ilqr_oracle.c): that checks the control flow, the lane
+// decomposition and the arithmetic order of the kernel source without a GPU.  It is never
+// linked into or called by the product (libilqr_b200.so has no CPU path).
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../ilqr_b200/csrc/ilqr_core.cuh"
+#include "../../ilqr_b200/csrc/params.h"
+
+using namespace ilqr;
+
+namespace {
+
+struct EmuBase {
+  virtual ~EmuBase() {}
+  virtual double init(const double *x0, const double *u0, int T) = 0;
+  virtual double warm_start(const double *x0) = 0;
+  virtual void iterate(int n) = 0;
+  virtual int backward_once(double lam) = 0;
+  virtual double rollout_once(double alpha) = 0;
+  virtual int get(int field, double *dst) = 0;
+  virtual double scalar(int which) = 0;
+  virtual long integer(int which) = 0;
+  int n = 0, m = 0;
+};
+
+template <class Model, typename S, int CD>
+struct Emu : EmuBase {
+  static constexpr int N = Model::N, M = Model::M;
+  ilqr_desc desc;
+  SolveParams<S> P;
+  Scratch<N, M, S> sc;
+  HostExec<N, S> ex;
+  std::vector<S> x0, xs, us, K, k, Vx0, Vxx0;
+  TrajState<S> st;
+  int T = 0;
+
+  explicit Emu(const ilqr_desc &d) : desc(d) {
+    n = N;
+    m = M;
+    memset(&sc, 0, sizeof(sc));
+    memset(&st, 0, sizeof(st));
+  }
+  TrajPtrs<S> ptrs() {
+    TrajPtrs<S> t;
+    t.x0 = x0.data();
+    t.xs = xs.data();
+    t.us = us.data();
+    t.K = K.data();
+    t.k = k.data();
+    t.Vx0 = Vx0.data();
+    t.Vxx0 = Vxx0.data();
+    t.st = &st;
+    return t;
+  }
+  Core<Model, S, CD, HostExec<N, S>> core() { return Core<Model, S, CD, HostExec<N, S>>(P, sc, ex, ptrs()); }
+
+  double init(const double *x0_, const double *u0_, int T_) override {
+    T = T_;
+    desc.T = T;
+    make_solve_params<S>(desc, &P);
+    x0.assign(N, 0);
+    xs.assign((size_t)(T + 1) * N, 0);
+    us.assign((size_t)T * M, 0);
+    K.assign((size_t)T * M * N, 0);
+    k.assign((size_t)T * M, 0);
+    Vx0.assign(N, 0);
+    Vxx0.assign(N * N, 0);
+    for (int i = 0; i < N; i++) x0[i] = S(x0_[i]);
+    for (int i = 0; i < T * M; i++) us[i] = S(u0_[i]);
+    core().op_init();
+    return st.cost;
+  }
+  double warm_start(const double *x0_) override {
+    for (int i = 0; i < N; i++) x0[i] = S(x0_[i]);
+    core().op_warm_start();
+    return st.cost;
+  }
+  void iterate(int cnt) override { core().op_iterate(cnt); }
+  int backward_once(double lam) override {
+    core().op_backward_once(S(lam));
+    return st.diverge;
+  }
+  double rollout_once(double alpha) override {
+    core().op_rollout_once(S(alpha));
+    return st.cost;
+  }
+  int get(int field, double *dst) override {
+    const std::vector<S> *v = nullptr;
+    switch (field) {
+      case 0: v = &xs; break;
+      case 1: v = &us; break;
+      case 2: v = &K; break;
+      case 3: v = &k; break;
+      case 4: dst[0] = st.cost; return 1;
+      case 5: dst[0] = st.dV0; dst[1] = st.dV1; return 2;
+      case 6: v = &Vx0; break;
+      case 7: v = &Vxx0; break;
+      default: return -1;
+    }
+    for (size_t i = 0; i < v->size(); i++) dst[i] = (*v)[i];
+    return (int)v->size();
+  }
+  double scalar(int which) override {
+    switch (which) {
+      case 0: return st.lam;
+      case 1: return st.dlam;
+      case 2: return st.gnorm;
+      case 3: return st.dcost;
+      case 4: return st.expected;
+      case 5: return st.alpha;
+      case 6: return st.new_cost;
+      default: return 0;
+    }
+  }
+  long integer(int which) override {
+    switch (which) {
+      case 0: return st.iter;
+      case 1: return st.trips;
+      case 2: return st.status;
+      case 3: return st.alpha_index;
+      case 4: return st.n_accept;
+      case 5: return st.n_reject;
+      case 6: return st.n_rollouts;
+      case 7: return st.n_backward;
+      case 8: return st.n_deriv;
+      case 9: return T;
+      case 10: return st.diverge;
+      default: return -1;
+    }
+  }
+};
+
+template <class Model, typename S>
+EmuBase *make_cd(const ilqr_desc &d) {
+  if (d.cost_deriv == ILQR_COST_ANALYTIC) return new Emu<Model, S, kCostAnalytic>(d);
+  return new Emu<Model, S, kCostFD>(d);
+}
+template <class Model>
+EmuBase *make_dtype(const ilqr_desc &d) {
+  if (d.dtype == ILQR_F32) return make_cd<Model, float>(d);
+  return make_cd<Model, double>(d);
+}
+
+template <int M>
+int run_qp(const ilqr_params &p, int generic, const double *Q, const double *c, const double *x0, const double *lo,
+           const double *hi, double *x_opt, int *v_free, double *R_free, int *r_dim) {
+  ilqr_desc d;
+  memset(&d, 0, sizeof(d));
+  d.params = p;
+  d.T = 1;
+  d.model_id = ILQR_MODEL_ACROBOT;
+  SolveParams<double> P;
+  make_solve_params<double>(d, &P);
+  static QPWork<M, double> w;
+  memset(&w, 0, sizeof(w));
+  for (int i = 0; i < M * M; i++) w.Q[i] = Q[i];
+  for (int i = 0; i < M; i++) {
+    w.c[i] = c[i];
+    w.x0[i] = x0[i];
+    w.lo[i] = lo[i];
+    w.hi[i] = hi[i];
+  }
+  if (generic) box_qp_generic<M, double>(P.qp, w);
+  else box_qp<M, double>(P.qp, w);
+  for (int i = 0; i < M; i++) {
+    x_opt[i] = w.x[i];
+    v_free[i] = w.v_free[i];
+  }
+  *r_dim = w.r_dim;
+  for (int i = 0; i < w.r_dim * w.r_dim; i++) R_free[i] = w.R[i];
+  return w.result;
+}
+
+}  // namespace
+
+extern "C" {
+
+void *emu_new(const ilqr_desc *d) {
+  if (d->model_id == ILQR_MODEL_ACROBOT) return make_dtype<Acrobot>(*d);
+  if (d->model_id == ILQR_MODEL_DOUBLE_INTEGRATOR) return make_dtype<DoubleIntegrator>(*d);
+  return nullptr;
+}
+void emu_free(void *h) { delete (EmuBase *)h; }
+void emu_dims(void *h, int *n, int *m) {
+  *n = ((EmuBase *)h)->n;
+  *m = ((EmuBase *)h)->m;
+}
+double emu_init(void *h, const double *x0, const double *u0, int T) { return ((EmuBase *)h)->init(x0, u0, T); }
+double emu_warm_start(void *h, const double *x0) { return ((EmuBase *)h)->warm_start(x0); }
+int emu_iterate(void *h, int n) {
+  ((EmuBase *)h)->iterate(n);
+  return 0;
+}
+int emu_backward_once(void *h, double lam) { return ((EmuBase *)h)->backward_once(lam); }
+double emu_rollout_once(void *h, double alpha) { return ((EmuBase *)h)->rollout_once(alpha); }
+int emu_get(void *h, int field, double *dst) { return ((EmuBase *)h)->get(field, dst); }
+double emu_scalar(void *h, int which) { return ((EmuBase *)h)->scalar(which); }
+long emu_int(void *h, int which) { return ((EmuBase *)h)->integer(which); }
+
+/* boxQP leaf: generic != 0 forces the general-m code path even for m == 1 */
+int emu_boxqp(const ilqr_params *p, int m, int generic, const double *Q, const double *c, const double *x0,
+              const double *lo, const double *hi, double *x_opt, int *v_free, double *R_free, int *r_dim) {
+  ilqr_params dp;
+  if (!p) {
+    default_params(&dp);
+    p = &dp;
+  }
+  switch (m) {
+    case 1: return run_qp<1>(*p, generic, Q, c, x0, lo, hi, x_opt, v_free, R_free, r_dim);
+    case 2: return run_qp<2>(*p, generic, Q, c, x0, lo, hi, x_opt, v_free, R_free, r_dim);
+    case 3: return run_qp<3>(*p, generic, Q, c, x0, lo, hi, x_opt, v_free, R_free, r_dim);
+    case 4: return run_qp<4>(*p, generic, Q, c, x0, lo, hi, x_opt, v_free, R_free, r_dim);
+    default: return -100;
+  }
+}
+
+}  // extern "C"

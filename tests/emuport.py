@@ -1,0 +1,135 @@
+"""ctypes view of tests/_build/libilqr_emu.so — the kernel core (ilqr_b200/csrc/ilqr_core.cuh)
+compiled for the CPU with the warp phases run lane by lane (tests/emu/ilqr_emu.cpp).
+
+Test infrastructure only: it lets the CPU suite check the kernel source's control flow and
+arithmetic order bit-for-bit against the oracle.  The product never loads it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from ilqr_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "tests", "_build", "libilqr_emu.so")
+SRC = os.path.join(ROOT, "tests", "emu", "ilqr_emu.cpp")
+DEPS = [SRC] + [os.path.join(ROOT, "ilqr_b200", "csrc", f) for f in
+                ("ilqr_core.cuh", "boxqp.cuh", "models.cuh", "params.h")] + [os.path.join(ROOT, "include", "ilqr_b200.h")]
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lib = None
+
+
+def build():
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
+                           "-Wno-unknown-pragmas", "-I" + os.path.join(ROOT, "include"), "-o", LIB_PATH, SRC])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in DEPS):
+            build()
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.emu_new.restype = vp
+        L.emu_new.argtypes = [C.POINTER(abi.Desc)]
+        L.emu_free.argtypes = [vp]
+        L.emu_dims.argtypes = [vp, _ip, _ip]
+        L.emu_init.restype = C.c_double
+        L.emu_init.argtypes = [vp, _dp, _dp, C.c_int]
+        L.emu_warm_start.restype = C.c_double
+        L.emu_warm_start.argtypes = [vp, _dp]
+        L.emu_iterate.argtypes = [vp, C.c_int]
+        L.emu_backward_once.argtypes = [vp, C.c_double]
+        L.emu_rollout_once.restype = C.c_double
+        L.emu_rollout_once.argtypes = [vp, C.c_double]
+        L.emu_get.argtypes = [vp, C.c_int, _dp]
+        L.emu_scalar.restype = C.c_double
+        L.emu_scalar.argtypes = [vp, C.c_int]
+        L.emu_int.restype = C.c_long
+        L.emu_int.argtypes = [vp, C.c_int]
+        L.emu_boxqp.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _arr(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class EmuSolver:
+    """Same surface as oracleport.OracleSolver (Vx/Vxx: timestep 0 only)."""
+
+    def __init__(self, model=abi.MODEL_ACROBOT, dt=0.02, goal=None, u_min=None, u_max=None,
+                 cost_deriv=abi.COST_FD, params=None, dtype=abi.F64):
+        self.desc = abi.make_desc(model=model, dt=dt, goal=goal, u_min=u_min, u_max=u_max, cost_deriv=cost_deriv,
+                                  params=params, dtype=dtype)
+        self.h = lib().emu_new(C.byref(self.desc))
+        assert self.h, "emu_new failed"
+        n, m = C.c_int(), C.c_int()
+        lib().emu_dims(self.h, C.byref(n), C.byref(m))
+        self.n, self.m, self.dt = n.value, m.value, dt
+        self.T = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().emu_free(self.h)
+            self.h = None
+
+    def init(self, x0, u0):
+        x0, u0 = _arr(x0), _arr(u0).reshape(-1, self.m)
+        self.T = u0.shape[0]
+        return lib().emu_init(self.h, _p(x0), _p(u0), self.T)
+
+    def warm_start(self, x0):
+        return lib().emu_warm_start(self.h, _p(_arr(x0)))
+
+    def iterate(self, n):
+        return lib().emu_iterate(self.h, n)
+
+    def backward_once(self, lam=1.0):
+        return lib().emu_backward_once(self.h, lam)
+
+    def rollout_once(self, alpha):
+        return lib().emu_rollout_once(self.h, alpha)
+
+    def get(self, name):
+        T, n, m = self.T, self.n, self.m
+        shapes = dict(xs=(T + 1, n), us=(T, m), K=(T, m, n), k=(T, m), cost=(1,), dV=(2,), Vx0=(n,), Vxx0=(n, n))
+        ids = dict(xs=0, us=1, K=2, k=3, cost=4, dV=5, Vx0=6, Vxx0=7)
+        out = np.empty(shapes[name], dtype=np.float64)
+        cnt = lib().emu_get(self.h, ids[name], _p(out))
+        assert cnt == out.size, (name, cnt, out.size)
+        return out
+
+    @property
+    def cost(self):
+        return float(self.get("cost")[0])
+
+    def scalar(self, name):
+        return lib().emu_scalar(self.h, dict(lam=0, dlam=1, gnorm=2, dcost=3, expected=4, alpha=5, new_cost=6)[name])
+
+    def count(self, name):
+        return int(lib().emu_int(self.h, dict(iter=0, loop_trips=1, status=2, alpha_index=3, accepts=4, rejects=5,
+                                              rollouts=6, backwards=7, derivs=8, T=9, diverge=10)[name]))
+
+
+def boxqp(Q, c, x0, lo, hi, params=None, generic=False):
+    Q, c, x0, lo, hi = map(_arr, (Q, c, x0, lo, hi))
+    m = c.size
+    x = np.empty(m)
+    vf = np.zeros(m, dtype=np.int32)
+    R = np.zeros(m * m)
+    rd = C.c_int()
+    res = lib().emu_boxqp(C.byref(params) if params is not None else None, m, int(generic), _p(Q), _p(c), _p(x0),
+                          _p(lo), _p(hi), _p(x), vf.ctypes.data_as(_ip), _p(R), C.byref(rd))
+    r = rd.value
+    return res, x, vf, R[:r * r].reshape(r, r)

@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ilqr_b200.solver -> libilqr_b200.so),
+against the CPU oracle (oracle/ilqr_oracle.c) on the same seeded inputs and against the golden
+vectors produced by the unmodified reference (tests/golden/).
+
+Tolerances.  BASELINE.json's north_star asks for 1e-6 relative on K, k and terminal cost.  The
+f64 kernels reproduce the oracle's arithmetic order without FMA, so
+  * the double integrator (no transcendental functions) must match the oracle BIT FOR BIT;
+  * the acrobot differs only through libdevice-vs-libm sin/cos (<= 2 ulp): a single backward pass
+    is compared at 1e-9, N-iteration checkpoints and terminal costs at 1e-6 (+1e-9 absolute floor,
+    SURVEY.md §7 "Parity methodology").
+"""
+import numpy as np
+import pytest
+
+from ilqr_b200 import abi
+from ilqr_b200.solver import BatchILQR, make_inputs
+
+import oracleport as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-6, 1e-9
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(a), np.abs(b))
+    err = np.abs(a - b)
+    ok = err <= rtol * scale + atol
+    assert ok.all(), "max abs err %.3e (rel %.3e) at %s" % (
+        err.max(), (err / np.maximum(scale, 1e-300)).max(), np.unravel_index(np.argmax(err - rtol * scale), err.shape))
+
+
+def oracle_batch(model, x0, u0, dt, n_iters, what, **kw):
+    """Run the oracle instance by instance; what(o) -> dict of arrays; returns dict of stacked arrays."""
+    outs = []
+    for b in range(x0.shape[0]):
+        o = O.OracleSolver(model, dt, **kw)
+        o.init(x0[b], u0[b])
+        if n_iters:
+            o.iterate(n_iters)
+        outs.append(what(o))
+    return {k: np.stack([d[k] for d in outs]) for k in outs[0]}
+
+
+def snap(o):
+    return dict(xs=o.get("xs"), us=o.get("us"), K=o.get("K"), k=o.get("k"), cost=np.float64(o.cost),
+                lam=np.float64(o.scalar("lam")), trips=np.int64(o.count("loop_trips")),
+                status=np.int64(o.count("status")), alpha_index=np.int64(o.count("alpha_index")))
+
+
+def gpu_snap(s):
+    return dict(xs=s.get("xs"), us=s.get("us"), K=s.get("K"), k=s.get("k"), cost=s.get("cost"), lam=s.get("lambda"),
+                trips=s.get("iters"), status=s.get("status"), alpha_index=s.get("alpha_index"))
+
+
+# ---------------------------------------------------------------------------------------------
+# acrobot, default limits (BASELINE configs 1/2), FD and analytic cost derivatives
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cost_deriv", [abi.COST_FD, abi.COST_ANALYTIC])
+def test_acrobot_single_phases(cost_deriv):
+    B, T = 8, 200
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cost_deriv)
+    c0 = s.init_traj(x0, u0)
+    ref = []
+    for b in range(B):
+        o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=cost_deriv)
+        ci = o.init(x0[b], u0[b])
+        xs_i = o.get("xs")
+        o.backward_once(1.0)
+        d = dict(c0=np.float64(ci), xs0=xs_i, K=o.get("K"), k=o.get("k"), dV=o.get("dV"), Vx0=o.get("Vx")[0],
+                 Vxx0=o.get("Vxx")[0], gnorm=np.float64(o.scalar("gnorm")), diverge=np.int64(o.count("diverge")))
+        d["rc"] = np.float64(o.rollout_once(0.5012))
+        d["xs1"], d["us1"] = o.get("xs"), o.get("us")
+        ref.append(d)
+    ref = {k: np.stack([d[k] for d in ref]) for k in ref[0]}
+    close(c0, ref["c0"], 1e-12, 0)
+    close(s.get("xs"), ref["xs0"], 1e-11, 1e-12)
+    s.backward_once(1.0)
+    assert (s.get("diverge") == ref["diverge"]).all()
+    for f in ("K", "k", "dV", "Vx0", "Vxx0", "gnorm"):
+        close(s.get(f), ref[f], 1e-9, 1e-10)
+    s.rollout_once(0.5012)
+    close(s.get("cost"), ref["rc"], 1e-9, 0)
+    close(s.get("xs"), ref["xs1"], 1e-8, 1e-9)
+    close(s.get("us"), ref["us1"], 1e-8, 1e-9)
+
+
+@pytest.mark.parametrize("cost_deriv", [abi.COST_FD, abi.COST_ANALYTIC])
+def test_acrobot_checkpoints(cost_deriv):
+    """K, k, xs, us, cost after N = 1, 5, 20 loop trips (SURVEY.md §7 parity methodology (ii))."""
+    B, T = 16, 200
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cost_deriv)
+    s.set_initial(x0, u0)
+    done = 0
+    for n in (1, 5, 20):
+        s.iterate(n - done)
+        done = n
+        ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, n, snap, cost_deriv=cost_deriv)
+        g = gpu_snap(s)
+        assert (g["trips"] == ref["trips"]).all()
+        assert (g["alpha_index"] == ref["alpha_index"]).all()
+        for f in ("cost", "lam", "xs", "us", "K", "k"):
+            close(g[f], ref[f])
+
+
+def test_acrobot_termination():
+    """Terminal cost at termination (parity methodology (iii)).  The last trips of a solve accept or
+    reject on the SIGN of a cost change that is pure rounding noise (src/ilqr_core.cpp:206), so the
+    trip count may legitimately differ by a few between two correct implementations; the terminal
+    cost may not."""
+    B, T = 32, 200
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02)
+    s.generate_trajectory(x0, u0)
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 101, snap)
+    g = gpu_snap(s)
+    assert (g["status"] != abi.RUNNING).all()
+    close(g["cost"], ref["cost"])
+    assert np.mean(g["trips"] == ref["trips"]) >= 0.75
+    assert np.abs(g["trips"] - ref["trips"]).max() <= 12
+    same = g["trips"] == ref["trips"]
+    close(g["xs"][same], ref["xs"][same])
+
+
+def test_acrobot_golden_reference(golden_solver):
+    """Against vectors written by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    g = golden_solver
+    cases = ["acrobot_T200_b%d" % b for b in range(6)]
+    x0 = np.stack([g[c + "/x0"] for c in cases])
+    u0 = np.stack([g[c + "/u0"] for c in cases])
+    s = BatchILQR(abi.MODEL_ACROBOT, T=200, B=len(cases), dt=0.02)
+    close(s.init_traj(x0, u0), [g[c + "/init_cost"] for c in cases], 1e-12, 0)
+    s.backward_once(1.0)
+    for f, name in (("K", "bw_K"), ("k", "bw_k"), ("dV", "bw_dV"), ("Vx0", "bw_Vx0"), ("Vxx0", "bw_Vxx0")):
+        close(s.get(f), np.stack([g[c + "/" + name] for c in cases]), 1e-8, 1e-9)
+    s.set_initial(x0, u0)
+    done = 0
+    for n in (1, 5, 20):
+        s.iterate(n - done)
+        done = n
+        for f in ("K", "k", "xs", "us"):
+            close(s.get(f), np.stack([g["%s/it%d_%s" % (c, n, f)] for c in cases]))
+        close(s.get("cost"), [g["%s/it%d_cost" % (c, n)] for c in cases])
+    s.solve()
+    close(s.get("cost"), [g[c + "/final_cost"] for c in cases])
+
+
+def test_acrobot_cli_T499(golden_solver):
+    """BASELINE config 1: the reference CLI's instance (src/run_ilqr.cpp:39-54), 100 iterations."""
+    g = golden_solver
+    c = "acrobot_cli_T499"
+    s = BatchILQR(abi.MODEL_ACROBOT, T=499, B=1, dt=0.02)
+    s.generate_trajectory(g[c + "/x0"][None], g[c + "/u0"][None])
+    assert s.get("status")[0] == abi.EXIT_MAXITER and s.get("iters")[0] == 100
+    close(s.get("cost")[0], g[c + "/final_cost"])
+    close(s.get("K")[0], g[c + "/final_K"])
+    close(s.get("k")[0], g[c + "/final_k"])
+    close(s.get("xs")[0], g[c + "/final_xs"])
+
+
+# ---------------------------------------------------------------------------------------------
+# control-limited acrobot (BASELINE config 4): boxQP path hot, lambda-max exits
+# ---------------------------------------------------------------------------------------------
+def test_acrobot_control_limited(golden_solver):
+    B, T = 16, 200
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    kw = dict(u_min=[-1.5], u_max=[1.5])
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, **kw)
+    s.set_initial(x0, u0)
+    done = 0
+    for n in (1, 5):
+        s.iterate(n - done)
+        done = n
+        ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, n, snap, **kw)
+        g = gpu_snap(s)
+        for f in ("cost", "lam", "xs", "us", "K", "k"):
+            close(g[f], ref[f])
+    s.solve()
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 101, snap, **kw)
+    close(s.get("cost"), ref["cost"])
+    assert (s.get("status") == ref["status"]).mean() >= 0.75
+    # the reference's golden: the rollouts are NOT clamped (src/ilqr_core.cpp:322-329)
+    gold = golden_solver
+    for b in range(3):
+        c = "acrobot_lim15_T200_b%d" % b
+        close(s.get("cost")[b], gold[c + "/final_cost"])
+    assert np.abs(s.get("us")).max() > 1.5
+
+
+# ---------------------------------------------------------------------------------------------
+# double integrator: no sin/cos, so the CUDA path must equal the oracle bit for bit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cost_deriv", [abi.COST_FD, abi.COST_ANALYTIC])
+def test_double_integrator_bit_exact(cost_deriv):
+    B, T, dt, goal = 12, 60, 0.05, [1.0, 1.0, 0.0, 0.0]
+    x0, u0 = make_inputs(12345, B, T, 4, 2, canonical_first=False)
+    s = BatchILQR(abi.MODEL_DOUBLE_INTEGRATOR, T=T, B=B, dt=dt, goal=goal, cost_deriv=cost_deriv)
+    s.set_initial(x0, u0)
+    ref0 = oracle_batch(abi.MODEL_DOUBLE_INTEGRATOR, x0, u0, dt, 0, snap, goal=goal, cost_deriv=cost_deriv)
+    assert (s.get("cost") == ref0["cost"]).all() and (s.get("xs") == ref0["xs"]).all()
+    done = 0
+    for n in (1, 3, 8, 101):
+        s.iterate(n - done)
+        done = n
+        ref = oracle_batch(abi.MODEL_DOUBLE_INTEGRATOR, x0, u0, dt, n, snap, goal=goal, cost_deriv=cost_deriv)
+        g = gpu_snap(s)
+        for f in ("trips", "status", "alpha_index", "cost", "lam", "xs", "us", "K", "k"):
+            assert (g[f] == ref[f]).all(), (n, f, np.abs(np.asarray(g[f], float) - np.asarray(ref[f], float)).max())
+
+
+def test_double_integrator_golden_cli(golden_solver):
+    g = golden_solver
+    c = "integrator_cli_T99"
+    s = BatchILQR(abi.MODEL_DOUBLE_INTEGRATOR, T=99, B=1, dt=0.02, goal=list(g[c + "/goal"]))
+    close(s.init_traj(g[c + "/x0"][None], g[c + "/u0"][None])[0], g[c + "/init_cost"], 1e-12, 0)
+    s.backward_once(1.0)
+    close(s.get("dV")[0], g[c + "/bw_dV"], 1e-8)
+    close(s.get("k")[0], g[c + "/bw_k"], 1e-8, 1e-10)
+    close(s.get("K")[0], g[c + "/bw_K"], 1e-7, 1e-9)
+    s.generate_trajectory(g[c + "/x0"][None], g[c + "/u0"][None])
+    close(s.get("cost")[0], g[c + "/final_cost"])
+
+
+# ---------------------------------------------------------------------------------------------
+# API semantics: warm start, iterate granularity, errors
+# ---------------------------------------------------------------------------------------------
+def test_warm_start_matches_oracle():
+    B, T = 4, 120
+    x0, u0 = make_inputs(777, B, T, 4, 1, canonical_first=False)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02)
+    s.set_initial(x0, u0)
+    s.iterate(6)
+    x0b = x0 + 0.01
+    s.warm_start(x0b)
+    cw = s.get("cost")
+    s.iterate(3)
+    for b in range(B):
+        o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02)
+        o.init(x0[b], u0[b])
+        o.iterate(6)
+        close(cw[b], o.warm_start(x0b[b]))
+        o.iterate(3)
+        close(s.get("cost")[b], o.cost)
+        close(s.get("xs")[b], o.get("xs"))
+        close(s.get("K")[b], o.get("K"))
+
+
+def test_iterate_granularity_and_determinism():
+    """iterate(1) x N == iterate(N) bit for bit; a trajectory's result does not depend on the batch around it."""
+    B, T = 64, 200
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    a = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    a.set_initial(x0, u0)
+    a.iterate(7)
+    b = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    b.set_initial(x0, u0)
+    for _ in range(7):
+        b.iterate(1)
+    for f in ("xs", "us", "K", "k", "cost", "lambda", "iters"):
+        assert (a.get(f) == b.get(f)).all(), f
+    sub = slice(5, 9)
+    c = BatchILQR(abi.MODEL_ACROBOT, T=T, B=4, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    c.set_initial(x0[sub], u0[sub])
+    c.iterate(7)
+    for f in ("xs", "us", "K", "k", "cost"):
+        assert (a.get(f)[sub] == c.get(f)).all(), f
+
+
+def test_errors():
+    with pytest.raises(Exception):
+        BatchILQR(model=7, T=10, B=1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=10, B=2)
+    with pytest.raises(Exception):
+        s.iterate(1)  # before set_initial
+    with pytest.raises(Exception):
+        s.get("cost")
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE config 2: B = 4096, T = 200, f64, analytic cost derivatives)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_config2_properties():
+    B, T = 4096, 200
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    c0 = s.init_traj(x0, u0)
+    s.solve()
+    cost, status, trips = s.get("cost"), s.get("status"), s.get("iters")
+    acc, rej = s.get("n_accept"), s.get("n_reject")
+    assert (status != abi.RUNNING).all()
+    assert np.isfinite(cost).all() and (cost <= c0 + 1e-9).all()          # monotone: only improving steps are accepted
+    assert ((acc + rej == trips) | (status == abi.EXIT_GRAD)).all()
+    assert (trips <= 100).all() and (trips >= 1).all()
+    # rolling the returned controls out open-loop reproduces the returned states and cost (consistency of xs/us/cost)
+    xs, us = s.get("xs"), s.get("us")
+    idx = np.random.default_rng(0).choice(B, 24, replace=False)
+    for b in idx:
+        o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC)
+        c = o.init(xs[b, 0], us[b])
+        close(c, cost[b], 1e-9, 1e-9)
+        close(o.get("xs"), xs[b], 1e-8, 1e-8)
+    # a sample of instances against the oracle's own solves
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0[idx], u0[idx], 0.02, 101, snap, cost_deriv=abi.COST_ANALYTIC)
+    close(cost[idx], ref["cost"])
+    # re-running is bit-reproducible
+    s2 = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    s2.generate_trajectory(x0, u0)
+    assert (s2.get("cost") == cost).all() and (s2.get("iters") == trips).all()
+
+
+def test_f32_config3_sanity():
+    """BASELINE config 3 arithmetic (f32, FD fx/fu, analytic cost derivatives) at a small batch: one backward
+    pass against the f64 oracle at f32-level tolerance, and the solve must reduce the cost."""
+    B, T = 32, 500
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, dtype=abi.F32, cost_deriv=abi.COST_ANALYTIC)
+    c0 = s.init_traj(x0, u0)
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 0, snap, cost_deriv=abi.COST_ANALYTIC)
+    close(c0, ref["cost"], 2e-4, 1e-3)
+    s.iterate(10)
+    c1 = s.get("cost")
+    assert np.isfinite(c1).all() and (c1 <= c0).all() and c1.mean() < 0.8 * c0.mean()
