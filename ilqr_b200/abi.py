@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "ilqr_b200", "libilqr_b200.so")
+LIB_PATH = os.environ.get("ILQR_B200_LIB") or os.path.join(ROOT, "ilqr_b200", "libilqr_b200.so")
 
 MAX_N, MAX_M, MAX_ALPHA = 8, 4, 16
 MODEL_ACROBOT, MODEL_DOUBLE_INTEGRATOR = 0, 1

@@ -34,6 +34,9 @@ namespace {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
+#ifndef ILQR_MIN_BLOCKS
+#define ILQR_MIN_BLOCKS 7 /* resident CTAs per SM the register allocation must allow */
+#endif
 
 enum Op { kOpInit = 0, kOpWarm = 1, kOpIterate = 2, kOpBackwardOnce = 3, kOpRolloutOnce = 4 };
 
@@ -50,13 +53,22 @@ struct KArgs {
   S scalar; /* lambda (backward_once) or alpha (rollout_once) */
 };
 
+/* shared memory of one warp: its scratch, then T gradient-norm terms; 16-byte granules */
+template <class Sc, typename S>
+__host__ __device__ inline size_t warp_smem_bytes(int T) {
+  return (sizeof(Sc) + (size_t)T * sizeof(S) + 15) & ~(size_t)15;
+}
+
 template <class Model, typename S, int CD>
-__global__ void __launch_bounds__(kThreads) ilqr_warp_kernel(const __grid_constant__ KArgs<S> a) {
+__global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) ilqr_warp_kernel(const __grid_constant__ KArgs<S> a) {
   constexpr int N = Model::N, M = Model::M;
-  using Sc = Scratch<N, M, S>;
+  using Sc = typename Core<Model, S, CD, WarpExec<N, M, S>>::Sc;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Sc &sc = reinterpret_cast<Sc *>(smem_raw)[threadIdx.x >> 5];
-  WarpExec<N, S> ex;
+  const size_t per_warp = warp_smem_bytes<Sc, S>(a.P.T);
+  unsigned char *mine = smem_raw + (threadIdx.x >> 5) * per_warp;
+  Sc &sc = *reinterpret_cast<Sc *>(mine);
+  S *gterm = reinterpret_cast<S *>(mine + sizeof(Sc));
+  WarpExec<N, M, S> ex;
   ex.lane = threadIdx.x & 31;
   const int T = a.P.T;
   for (;;) {
@@ -73,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) ilqr_warp_kernel(const __grid_consta
     tr.Vx0 = a.Vx0 + b * N;
     tr.Vxx0 = a.Vxx0 + b * N * N;
     tr.st = a.st + b;
-    Core<Model, S, CD, WarpExec<N, S>> core(a.P, sc, ex, tr);
+    Core<Model, S, CD, WarpExec<N, M, S>> core(a.P, sc, gterm, ex, tr);
     switch (a.op) {
       case kOpInit: core.op_init(); break;
       case kOpWarm: core.op_warm_start(); break;
@@ -175,7 +187,7 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
   a.n_iters = n_iters;
   a.scalar = S(scalar);
   auto kern = ilqr_warp_kernel<Model, S, CD>;
-  const size_t smem = sizeof(Scratch<N, M, S>) * kWarpsPerCta;
+  const size_t smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S>>::Sc, S>(h->desc.T) * kWarpsPerCta;
   if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));

@@ -38,6 +38,8 @@
 #ifndef ILQR_CORE_CUH_
 #define ILQR_CORE_CUH_
 
+#include <type_traits>
+
 #include "boxqp.cuh"
 #include "models.cuh"
 
@@ -85,7 +87,41 @@ struct TrajPtrs {
 };
 
 /* the warp's working set */
-template <int N, int M, typename S>
+#if defined(__CUDACC__)
+#define ILQR_HDC __host__ __device__ constexpr
+#else
+#define ILQR_HDC constexpr
+#endif
+ILQR_HDC int popc_(unsigned v) { return v ? (int)(v & 1u) + popc_(v >> 1) : 0; }
+
+/* f(integral_constant<int, 0>) ... f(integral_constant<int, G-1>): loops whose index must be a
+ * compile-time constant (so per-model tables fold to literals in device code) */
+template <int G, class F>
+ILQR_HD void static_for(F &&f) {
+  if constexpr (G > 0) {
+    static_for<G - 1>(f);
+    f(std::integral_constant<int, G - 1>{});
+  }
+}
+ILQR_HD int popcnt(unsigned v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+
+/* finite-difference variants of the model's trig arguments: argument g is needed at the base point
+ * and at +-eps on each state variable it depends on */
+template <class Model>
+struct TrigVariants {
+  static constexpr int KT = Model::kTrig;
+  static ILQR_HDC int count(int g) { return 1 + 2 * popc_(Model::trig_deps(g)); }
+  static ILQR_HDC int offset(int g) { return g <= 0 ? 0 : offset(g - 1) + count(g - 1); }
+  static constexpr int total = offset(KT);
+};
+
+template <int N, int M, typename S, int NTV = 1, int KT = 1>
 struct Scratch {
   static constexpr int NM = N + M;
   /* staged tiles */
@@ -102,23 +138,25 @@ struct Scratch {
   S Kc[M * N], kc[M], kprev[M];
   S Vtmp[N * N], Vxn[N];
   S newcost[kMaxAlpha];
+  S bsn[NTV > 0 ? NTV : 1], bcs[NTV > 0 ? NTV : 1];                   /* backward: sincos per (argument, FD variant) */
   QPWork<M, S> qp;
   TrajState<S> st;
   int flag;
 };
 
-template <int N, typename S>
+template <int N, int M, typename S>
 struct LaneRegs {
   S x[N];
+  S uc[M];
   S cost;
   S gn;
 };
 
 #if defined(__CUDACC__)
 /* device: the calling thread is one lane; a phase ends with a warp barrier */
-template <int N, typename S>
+template <int N, int M, typename S>
 struct WarpExec {
-  LaneRegs<N, S> regs;
+  LaneRegs<N, M, S> regs;
   int lane;
   template <class Fn>
   __device__ __forceinline__ void lanes(Fn fn) {
@@ -128,9 +166,9 @@ struct WarpExec {
 };
 #endif
 /* host (tests only): run the phase for lane 0..31 in turn */
-template <int N, typename S>
+template <int N, int M, typename S>
 struct HostExec {
-  LaneRegs<N, S> regs[32];
+  LaneRegs<N, M, S> regs[32];
   template <class Fn>
   void lanes(Fn fn) {
     for (int l = 0; l < 32; l++) fn(l, regs[l]);
@@ -140,15 +178,18 @@ struct HostExec {
 template <class Model, typename S, int CD, class Exec>
 struct Core {
   static constexpr int N = Model::N, M = Model::M, NM = N + M;
-  using Sc = Scratch<N, M, S>;
-  using Lane = LaneRegs<N, S>;
+  static constexpr int KT = Model::kTrig;
+  using TV = TrigVariants<Model>;
+  using Sc = Scratch<N, M, S, TV::total, KT>;
+  using Lane = LaneRegs<N, M, S>;
 
   const SolveParams<S> &P;
   Sc &sc;
   Exec &ex;
   TrajPtrs<S> tr;
+  S *gterm; /* [T] per-timestep terms of the gradient norm, in the warp's shared memory after the scratch */
 
-  ILQR_HD Core(const SolveParams<S> &p, Sc &s, Exec &e, const TrajPtrs<S> &t) : P(p), sc(s), ex(e), tr(t) {}
+  ILQR_HD Core(const SolveParams<S> &p, Sc &s, S *g, Exec &e, const TrajPtrs<S> &t) : P(p), sc(s), ex(e), tr(t), gterm(g) {}
 
   /* ---- tiles ---------------------------------------------------------------------------- */
   ILQR_HD void copy_in(S *dst, const S *src, int count) {
@@ -267,26 +308,78 @@ struct Core {
     }
   }
 
-  /* Phase: derivatives of timestep i at (sc.x, sc.u) -> sc.E (perturbed steps), sc.c* */
+  /* Phase: derivatives of timestep i at (sc.x, sc.u) -> sc.E (perturbed steps), sc.c*.
+   * Two sub-phases when the model has trig arguments: every (argument, variant) sincos on its own
+   * lane (the cost derivatives ride along on the lanes after those), then the 2(n+m) perturbed
+   * Euler steps from the tabulated values. */
   ILQR_HD void phase_derivatives() {
+    constexpr int nDyn = 2 * NM;
+    constexpr int nCost = (CD == kCostFD) ? kStencilStep : 1;
+    constexpr int nTrig = TV::total;
     ex.lanes([&](int lane, Lane &) {
-      constexpr int nDyn = 2 * NM;
-      constexpr int nCost = (CD == kCostFD) ? kStencilStep : 1;
-      for (int task = lane; task < nDyn + nCost; task += 32) {
-        if (task < nDyn) { /* finite_diff_jacobian of integrate_dynamics, finite_diff.h:35-47 */
-          const int var = task >> 1;
-          const S d = (task & 1) ? -P.fd_eps : P.fd_eps;
-          S xa[N], ua[M], x1[N];
-          perturb<N>(sc.x, var, d, -1, S(0), xa);
-          perturb<M>(sc.u, var - N, d, -1, S(0), ua);
-          integrate<Model, S>(xa, ua, P.mp, P.dt, x1);
+      for (int task = lane; task < nTrig + nCost; task += 32) {
+        if (KT > 0 && task < nTrig) {
+          if constexpr (KT > 0) {
+          int g = 0, off = 0;
+          unsigned deps = 0;
+          static_for<KT>([&](auto gc) {
+            constexpr int G = decltype(gc)::value;
+            constexpr int o = TV::offset(G);
+            constexpr unsigned dd = Model::trig_deps(G);
+            if (task >= o) {
+              g = G;
+              off = o;
+              deps = dd;
+            }
+          });
+          const int v = task - off;
+          int var = -1;
+          S d = 0;
+          if (v > 0) {
+            int rank = (v - 1) >> 1, seen = 0;
 #pragma unroll
-          for (int r = 0; r < N; r++) sc.E[task * N + r] = x1[r];
+            for (int q = 0; q < N; q++)
+              if ((deps >> q) & 1u) {
+                if (seen == rank) var = q;
+                seen++;
+              }
+            d = ((v - 1) & 1) ? -P.fd_eps : P.fd_eps;
+          }
+          S xa[N];
+          perturb<N>(sc.x, var, d, -1, S(0), xa);
+          sincos_det(Model::trig_arg(g, xa), &sc.bsn[task], &sc.bcs[task]);
+          }
         } else if (CD == kCostFD) {
-          cost_stencil(task - nDyn, false);
+          cost_stencil(task - nTrig, false);
         } else {
           Model::cost_derivs(sc.x, sc.u, P.mp, false, sc.cx, sc.cu, sc.cxx, sc.cxu, sc.cuu);
         }
+      }
+    });
+    ex.lanes([&](int lane, Lane &) {
+      for (int task = lane; task < nDyn; task += 32) { /* finite_diff_jacobian of integrate_dynamics, finite_diff.h:35-47 */
+        const int var = task >> 1, neg = task & 1;
+        const S d = neg ? -P.fd_eps : P.fd_eps;
+        S xa[N], ua[M], x1[N];
+        perturb<N>(sc.x, var, d, -1, S(0), xa);
+        perturb<M>(sc.u, var - N, d, -1, S(0), ua);
+        if constexpr (KT > 0) {
+          S sn[KT], cs[KT];
+          static_for<KT>([&](auto gc) { /* variant 0 = base value when the argument does not depend on `var` */
+            constexpr int G = decltype(gc)::value;
+            constexpr int o = TV::offset(G);
+            constexpr unsigned dd = Model::trig_deps(G);
+            int variant = 0;
+            if (var < N && ((dd >> var) & 1u)) variant = 1 + 2 * popcnt(dd & ((1u << var) - 1u)) + neg;
+            sn[G] = sc.bsn[o + variant];
+            cs[G] = sc.bcs[o + variant];
+          });
+          integrate_trig<Model, S>(xa, ua, P.mp, P.dt, sn, cs, x1);
+        } else {
+          integrate<Model, S>(xa, ua, P.mp, P.dt, x1);
+        }
+#pragma unroll
+        for (int r = 0; r < N; r++) sc.E[task * N + r] = x1[r];
       }
     });
   }
@@ -508,9 +601,10 @@ struct Core {
           return t0 + tt;
         }
         ex.lanes([&](int lane, Lane &) {
-          for (int e = lane; e < M * N + M; e += 32) {
+          for (int e = lane; e < M * N + M + 1; e += 32) {
             if (e < M * N) sc.K[tt * M * N + e] = sc.Kc[e];
-            else sc.k[tt * M + e - M * N] = sc.kc[e - M * N];
+            else if (e < M * N + M) sc.k[tt * M + e - M * N] = sc.kc[e - M * N];
+            else gterm[t0 + tt] = gn_term(sc.kc, sc.u);
           }
         });
       }
@@ -540,6 +634,16 @@ struct Core {
       sc.st.gnorm = acc / T;
     });
   }
+  /* the same number from the terms the backward pass just left in gterm (ascending t, like the reference) */
+  ILQR_HD void gradient_norm_from_terms() {
+    const int T = P.T;
+    ex.lanes([&](int lane, Lane &) {
+      if (lane != 0) return;
+      S acc = 0;
+      for (int t = 0; t < T; t++) acc += gterm[t];
+      sc.st.gnorm = acc / T;
+    });
+  }
   ILQR_HD static S gn_term(const S *k, const S *u) {
     S mx = -INFINITY;
 #pragma unroll
@@ -552,9 +656,8 @@ struct Core {
 
   /* ---- rollouts ------------------------------------------------------------------------- */
 
-  /* one step of iLQR::forward_pass (:314-326) for one lane; returns the applied control in uc */
-  ILQR_HD void rollout_step(Lane &L, const S *xhat, const S *ubar, const S *kt, const S *Kt, S alpha, int mode,
-                            S *uc) {
+  /* one step of iLQR::forward_pass (:314-326) for one lane; the applied control is left in L.uc */
+  ILQR_HD void rollout_step(Lane &L, const S *xhat, const S *ubar, const S *kt, const S *Kt, S alpha, int mode) {
 #pragma unroll
     for (int j = 0; j < M; j++) {
       S v = ubar[j];
@@ -565,11 +668,11 @@ struct Core {
         for (int i = 0; i < N; i++) a += Kt[j * N + i] * (L.x[i] - xhat[i]);
         v += a;
       }
-      uc[j] = v;
+      L.uc[j] = v;
     }
-    L.cost += Model::cost(L.x, uc, P.mp); /* :324 */
+    L.cost += Model::cost(L.x, L.uc, P.mp); /* :324 */
     S x1[N];
-    integrate<Model, S>(L.x, uc, P.mp, P.dt, x1); /* :325 */
+    integrate<Model, S>(L.x, L.uc, P.mp, P.dt, x1); /* :325 */
 #pragma unroll
     for (int i = 0; i < N; i++) L.x[i] = x1[i];
   }
@@ -585,34 +688,29 @@ struct Core {
     });
   }
 
-  /* The candidate rollouts of the line search, lane a <-> alpha[a]; costs land in sc.newcost and
-   * the gradient norm (:405-412, ascending t like the reference) in sc.st.gnorm. */
+  /* The candidate rollouts of the line search, lane a <-> alpha[a]; costs land in sc.newcost. */
   ILQR_HD void rollout_candidates() {
     const int T = P.T;
+    const int na = P.n_alpha;
     ex.lanes([&](int lane, Lane &L) {
 #pragma unroll
       for (int i = 0; i < N; i++) L.x[i] = tr.x0[i];
       L.cost = 0;
-      L.gn = 0;
     });
     for (int t0 = 0; t0 < T; t0 += kTile) {
       const int cnt = (T - t0 < kTile) ? T - t0 : kTile;
       load_forward_tile(t0, cnt, kRollClosed);
       ex.lanes([&](int lane, Lane &L) {
-        if (lane >= P.n_alpha) return;
+        if (lane >= na) return;
         const S alpha = P.alpha[lane];
-        for (int tt = 0; tt < cnt; tt++) {
-          S uc[M];
-          L.gn += gn_term(sc.k + tt * M, sc.us + tt * M);
-          rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, kRollClosed, uc);
-        }
+        for (int tt = 0; tt < cnt; tt++)
+          rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, kRollClosed);
       });
     }
     ex.lanes([&](int lane, Lane &L) {
-      if (lane >= P.n_alpha) return;
+      if (lane >= na) return;
       L.cost += Model::final_cost(L.x, P.mp); /* :335 */
       sc.newcost[lane] = L.cost;
-      if (lane == 0) sc.st.gnorm = L.gn / T;
     });
   }
 
@@ -634,10 +732,9 @@ struct Core {
         for (int tt = 0; tt < cnt; tt++) {
 #pragma unroll
           for (int i = 0; i < N; i++) sc.xn[tt * N + i] = L.x[i];
-          S uc[M];
-          rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, mode, uc);
+          rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, mode);
 #pragma unroll
-          for (int j = 0; j < M; j++) sc.un[tt * M + j] = uc[j];
+          for (int j = 0; j < M; j++) sc.un[tt * M + j] = L.uc[j];
         }
       });
       ex.lanes([&](int lane, Lane &) {
@@ -715,7 +812,8 @@ struct Core {
       sc.st.lam = lam;
       sc.st.diverge = d;
     });
-    gradient_norm_only();
+    if (d == 0) gradient_norm_from_terms();
+    else gradient_norm_only();
     store_state();
   }
 
@@ -766,8 +864,12 @@ struct Core {
         }
         back_done = true;
       }
-      if (back_done) rollout_candidates(); /* also yields gnorm */
-      else gradient_norm_only();
+      if (back_done) {
+        gradient_norm_from_terms();
+        rollout_candidates();
+      } else {
+        gradient_norm_only();
+      }
       /* :153-159, then the acceptance test :199-213 in the reference's serial order */
       ex.lanes([&](int lane, Lane &) {
         if (lane != 0) return;

@@ -1,0 +1,100 @@
+/*
+ * trig.cuh — sin and cos of one argument, evaluated together, with IDENTICAL results on the GPU
+ * and on the host.
+ *
+ * Why not ::sin / ::cos.  libdevice's and glibc's double-precision sin/cos each stay within 1–2 ulp
+ * of the true value but not of each other, so any check of the kernels against a CPU run of the
+ * same source could only ever be approximate; and they are the most expensive thing in an acrobot
+ * dynamics evaluation (four calls, ~65 SASS instructions each: 41 % of the warp instructions of
+ * the first version of the solve kernel, profiles/r1a).  This header restates the classic
+ * fdlibm/musl algorithm — Cody–Waite reduction by pi/2 in two 33-bit steps, then the degree-13 /
+ * degree-14 minimax kernels with the reduction tail folded in — using only IEEE-754 operations
+ * whose result is defined bit for bit (add, multiply, explicitly fused multiply-add, rint), so
+ * g++ (tests/emu, -ffp-contract=off) and nvcc (-fmad=false) produce the same doubles.  Error
+ * < 1 ulp, the same class as the reference's libm (checked against it in tests/test_trig.py).
+ *
+ * |x| >= 2^19 * pi/2 (a blown-up rollout) falls back to the platform's sincos: still correct, no
+ * longer bit-reproducible between host and device.
+ */
+#ifndef ILQR_TRIG_CUH_
+#define ILQR_TRIG_CUH_
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define ILQR_HD __host__ __device__ __forceinline__
+#else
+#define ILQR_HD inline __attribute__((always_inline))
+#endif
+
+namespace ilqr {
+
+/* fdlibm e_rem_pio2.c / k_sin.c / k_cos.c constants.  On the device they sit in constant memory so
+ * the DFMAs take them as c[bank][offset] operands; as literals the compiler materialised each one
+ * with two UMOVs before use (a third of the instructions of this function, profiles/r1c). */
+#define ILQR_TRIG_TABLE                                                                                              \
+  {6.36619772367581382433e-01 /* invpio2 0x3FE45F306DC9C883 */, 1.57079632673412561417e+00 /* pio2_1 0x3FF921FB54400000 */, \
+   6.07710050630396597660e-11 /* pio2_2 0x3DD0B4611A600000 */, 2.02226624879595063154e-21 /* pio2_2t 0x3BA3198A2E037073 */, \
+   -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,   \
+   -2.50507602534068634195e-08, 1.58969099521155010221e-10, /* S1..S6 */                                              \
+   4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,  \
+   2.08757232129817482790e-09, -1.13596475577881948265e-11 /* C1..C6 */}
+#if defined(__CUDACC__)
+__constant__ double kTrigDev[16] = ILQR_TRIG_TABLE;
+#endif
+static const double kTrigHost[16] = ILQR_TRIG_TABLE;
+
+#if defined(__CUDACC__) && defined(ILQR_NOINLINE_TRIG)
+#define ILQR_HD_TRIG __host__ __device__ __noinline__
+#else
+#define ILQR_HD_TRIG ILQR_HD
+#endif
+
+ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
+#if defined(ILQR_TRIG_LIBM) && !defined(__CUDACC__)
+  /* tests/emu only: the platform libm, to compare the kernel source bit for bit with the oracle */
+  *sn = ::sin(x);
+  *cs = ::cos(x);
+  return;
+#endif
+#if defined(__CUDA_ARCH__)
+  const double *tab = kTrigDev;
+#else
+  const double *tab = kTrigHost;
+#endif
+  const double invpio2 = tab[0], pio2_1 = tab[1], pio2_2 = tab[2], pio2_2t = tab[3];
+  const double S1 = tab[4], S2 = tab[5], S3 = tab[6], S4 = tab[7], S5 = tab[8], S6 = tab[9];
+  const double C1 = tab[10], C2 = tab[11], C3 = tab[12], C4 = tab[13], C5 = tab[14], C6 = tab[15];
+  if (!(::fabs(x) < 8.0e5)) { /* also catches NaN */
+    ::sincos(x, sn, cs);
+    return;
+  }
+  /* x = n * pi/2 + (y0 + y1), |y0| <= pi/4 (+ rounding), 118-bit pi/2 */
+  const double fn = ::rint(x * invpio2);
+  const int n = (int)fn;
+  const double t = ::fma(-fn, pio2_1, x);
+  double w = fn * pio2_2;
+  const double r = t - w;
+  w = ::fma(fn, pio2_2t, -((t - r) - w));
+  const double y0 = r - w;
+  const double y1 = (r - y0) - w;
+  /* kernels on [-pi/4, pi/4] with tail y1 */
+  const double z = y0 * y0;
+  const double v = z * y0;
+  const double ps = ::fma(z, ::fma(z, ::fma(z, ::fma(z, S6, S5), S4), S3), S2);
+  const double ks = y0 - ((::fma(z, ::fma(-v, ps, 0.5 * y1), -y1)) - v * S1);
+  const double pc = z * ::fma(z, ::fma(z, ::fma(z, ::fma(z, ::fma(z, C6, C5), C4), C3), C2), C1);
+  const double hz = 0.5 * z;
+  const double wc = 1.0 - hz;
+  const double kc = wc + (((1.0 - wc) - hz) + ::fma(z, pc, -(y0 * y1)));
+  /* quadrant */
+  const double a = (n & 1) ? kc : ks;
+  const double b = (n & 1) ? ks : kc;
+  *sn = (n & 2) ? -a : a;
+  *cs = ((n + 1) & 2) ? -b : b;
+}
+
+ILQR_HD void sincos_det(float x, float *sn, float *cs) { ::sincosf(x, sn, cs); }
+
+}  // namespace ilqr
+#endif

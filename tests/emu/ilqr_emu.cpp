@@ -36,9 +36,9 @@ struct Emu : EmuBase {
   static constexpr int N = Model::N, M = Model::M;
   ilqr_desc desc;
   SolveParams<S> P;
-  Scratch<N, M, S> sc;
-  HostExec<N, S> ex;
-  std::vector<S> x0, xs, us, K, k, Vx0, Vxx0;
+  typename Core<Model, S, CD, HostExec<N, M, S>>::Sc sc;
+  HostExec<N, M, S> ex;
+  std::vector<S> x0, xs, us, K, k, Vx0, Vxx0, gterm;
   TrajState<S> st;
   int T = 0;
 
@@ -60,7 +60,7 @@ struct Emu : EmuBase {
     t.st = &st;
     return t;
   }
-  Core<Model, S, CD, HostExec<N, S>> core() { return Core<Model, S, CD, HostExec<N, S>>(P, sc, ex, ptrs()); }
+  Core<Model, S, CD, HostExec<N, M, S>> core() { return Core<Model, S, CD, HostExec<N, M, S>>(P, sc, gterm.data(), ex, ptrs()); }
 
   double init(const double *x0_, const double *u0_, int T_) override {
     T = T_;
@@ -73,6 +73,7 @@ struct Emu : EmuBase {
     k.assign((size_t)T * M, 0);
     Vx0.assign(N, 0);
     Vxx0.assign(N * N, 0);
+    gterm.assign(T, 0);
     for (int i = 0; i < N; i++) x0[i] = S(x0_[i]);
     for (int i = 0; i < T * M; i++) us[i] = S(u0_[i]);
     core().op_init();

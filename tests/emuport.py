@@ -13,27 +13,30 @@ import numpy as np
 from ilqr_b200 import abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "tests", "_build", "libilqr_emu.so")
+LIB_PATH = os.path.join(ROOT, "tests", "_build", "libilqr_emu.so")            # same sin/cos as the CUDA build
+LIB_PATH_LIBM = os.path.join(ROOT, "tests", "_build", "libilqr_emu_libm.so")  # platform libm sin/cos (= the oracle's)
 SRC = os.path.join(ROOT, "tests", "emu", "ilqr_emu.cpp")
 DEPS = [SRC] + [os.path.join(ROOT, "ilqr_b200", "csrc", f) for f in
-                ("ilqr_core.cuh", "boxqp.cuh", "models.cuh", "params.h")] + [os.path.join(ROOT, "include", "ilqr_b200.h")]
+                ("ilqr_core.cuh", "boxqp.cuh", "models.cuh", "trig.cuh", "params.h")] + [os.path.join(ROOT, "include", "ilqr_b200.h")]
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
-_lib = None
+_libs = {}
 
 
-def build():
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+def build(libm=False):
+    path = LIB_PATH_LIBM if libm else LIB_PATH
+    os.makedirs(os.path.dirname(path), exist_ok=True)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
-                           "-Wno-unknown-pragmas", "-I" + os.path.join(ROOT, "include"), "-o", LIB_PATH, SRC])
+                           "-Wno-unknown-pragmas", "-I" + os.path.join(ROOT, "include")] +
+                          (["-DILQR_TRIG_LIBM"] if libm else []) + ["-o", path, SRC])
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in DEPS):
-            build()
-        L = C.CDLL(LIB_PATH)
+def lib(libm=False):
+    if libm not in _libs:
+        path = LIB_PATH_LIBM if libm else LIB_PATH
+        if (not os.path.exists(path)) or any(os.path.getmtime(d) > os.path.getmtime(path) for d in DEPS):
+            build(libm)
+        L = C.CDLL(path)
         vp = C.c_void_p
         L.emu_new.restype = vp
         L.emu_new.argtypes = [C.POINTER(abi.Desc)]
@@ -53,8 +56,8 @@ def lib():
         L.emu_int.restype = C.c_long
         L.emu_int.argtypes = [vp, C.c_int]
         L.emu_boxqp.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
-        _lib = L
-    return _lib
+        _libs[libm] = L
+    return _libs[libm]
 
 
 def _p(a):
@@ -69,44 +72,45 @@ class EmuSolver:
     """Same surface as oracleport.OracleSolver (Vx/Vxx: timestep 0 only)."""
 
     def __init__(self, model=abi.MODEL_ACROBOT, dt=0.02, goal=None, u_min=None, u_max=None,
-                 cost_deriv=abi.COST_FD, params=None, dtype=abi.F64):
+                 cost_deriv=abi.COST_FD, params=None, dtype=abi.F64, libm=False):
+        self.L = lib(libm)
         self.desc = abi.make_desc(model=model, dt=dt, goal=goal, u_min=u_min, u_max=u_max, cost_deriv=cost_deriv,
                                   params=params, dtype=dtype)
-        self.h = lib().emu_new(C.byref(self.desc))
+        self.h = self.L.emu_new(C.byref(self.desc))
         assert self.h, "emu_new failed"
         n, m = C.c_int(), C.c_int()
-        lib().emu_dims(self.h, C.byref(n), C.byref(m))
+        self.L.emu_dims(self.h, C.byref(n), C.byref(m))
         self.n, self.m, self.dt = n.value, m.value, dt
         self.T = 0
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().emu_free(self.h)
+            self.L.emu_free(self.h)
             self.h = None
 
     def init(self, x0, u0):
         x0, u0 = _arr(x0), _arr(u0).reshape(-1, self.m)
         self.T = u0.shape[0]
-        return lib().emu_init(self.h, _p(x0), _p(u0), self.T)
+        return self.L.emu_init(self.h, _p(x0), _p(u0), self.T)
 
     def warm_start(self, x0):
-        return lib().emu_warm_start(self.h, _p(_arr(x0)))
+        return self.L.emu_warm_start(self.h, _p(_arr(x0)))
 
     def iterate(self, n):
-        return lib().emu_iterate(self.h, n)
+        return self.L.emu_iterate(self.h, n)
 
     def backward_once(self, lam=1.0):
-        return lib().emu_backward_once(self.h, lam)
+        return self.L.emu_backward_once(self.h, lam)
 
     def rollout_once(self, alpha):
-        return lib().emu_rollout_once(self.h, alpha)
+        return self.L.emu_rollout_once(self.h, alpha)
 
     def get(self, name):
         T, n, m = self.T, self.n, self.m
         shapes = dict(xs=(T + 1, n), us=(T, m), K=(T, m, n), k=(T, m), cost=(1,), dV=(2,), Vx0=(n,), Vxx0=(n, n))
         ids = dict(xs=0, us=1, K=2, k=3, cost=4, dV=5, Vx0=6, Vxx0=7)
         out = np.empty(shapes[name], dtype=np.float64)
-        cnt = lib().emu_get(self.h, ids[name], _p(out))
+        cnt = self.L.emu_get(self.h, ids[name], _p(out))
         assert cnt == out.size, (name, cnt, out.size)
         return out
 
@@ -115,10 +119,10 @@ class EmuSolver:
         return float(self.get("cost")[0])
 
     def scalar(self, name):
-        return lib().emu_scalar(self.h, dict(lam=0, dlam=1, gnorm=2, dcost=3, expected=4, alpha=5, new_cost=6)[name])
+        return self.L.emu_scalar(self.h, dict(lam=0, dlam=1, gnorm=2, dcost=3, expected=4, alpha=5, new_cost=6)[name])
 
     def count(self, name):
-        return int(lib().emu_int(self.h, dict(iter=0, loop_trips=1, status=2, alpha_index=3, accepts=4, rejects=5,
+        return int(self.L.emu_int(self.h, dict(iter=0, loop_trips=1, status=2, alpha_index=3, accepts=4, rejects=5,
                                               rollouts=6, backwards=7, derivs=8, T=9, diverge=10)[name]))
 
 

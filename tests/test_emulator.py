@@ -1,0 +1,122 @@
+"""CPU: the KERNEL SOURCE (ilqr_b200/csrc/ilqr_core.cuh + boxqp.cuh + models.cuh) compiled with g++
+and run lane by lane (tests/emu), against the oracle.
+
+  * with the platform libm for sin/cos (-DILQR_TRIG_LIBM) the kernel source must reproduce the
+    oracle BIT FOR BIT — every array, every scalar, every counter, at every loop trip — for both
+    models, both cost-derivative modes and the control-limited case: the lane decomposition and
+    the arithmetic order of the warp code are exactly the reference's;
+  * with the deterministic sincos the CUDA build uses (trig.cuh) the double integrator stays
+    bit-exact and the acrobot moves by the sin/cos noise floor, which this file measures.
+The GPU suite then checks the real kernels bit for bit against this same CPU build.
+"""
+import numpy as np
+import pytest
+
+from ilqr_b200 import abi
+from ilqr_b200.solver import ILQRError  # noqa: F401  (import check only; no CUDA call)
+
+import emuport as E
+import oracleport as O
+
+ARR = ("xs", "us", "K", "k")
+SCAL = ("lam", "dlam", "gnorm", "dcost", "expected", "alpha", "new_cost")
+CNT = ("iter", "loop_trips", "status", "alpha_index", "accepts", "rejects", "rollouts", "backwards", "derivs", "diverge")
+
+
+def lockstep(model, x0, u0, dt, libm, max_trips=101, **kw):
+    o, e = O.OracleSolver(model, dt, **kw), E.EmuSolver(model, dt, libm=libm, **kw)
+    assert o.init(x0, u0) == e.init(x0, u0)
+    assert np.array_equal(o.get("xs"), e.get("xs"))
+    assert o.backward_once(1.0) == e.backward_once(1.0)
+    for f in ("K", "k", "dV"):
+        assert np.array_equal(o.get(f), e.get(f)), f
+    assert np.array_equal(o.get("Vx")[0], e.get("Vx0")) and np.array_equal(o.get("Vxx")[0], e.get("Vxx0"))
+    assert o.scalar("gnorm") == e.scalar("gnorm")
+    assert o.rollout_once(0.5012) == e.rollout_once(0.5012)
+    o.init(x0, u0)
+    e.init(x0, u0)
+    for trip in range(max_trips):
+        o.iterate(1)
+        e.iterate(1)
+        for f in ARR:
+            assert np.array_equal(o.get(f), e.get(f)), (trip, f)
+        for f in SCAL:
+            assert o.scalar(f) == e.scalar(f), (trip, f)
+        for f in CNT:
+            assert o.count(f) == e.count(f), (trip, f)
+        assert o.cost == e.cost
+        if o.count("status") != 0:
+            break
+    return o.count("loop_trips")
+
+
+@pytest.mark.parametrize("case,cd,kw", [
+    ("acrobot_T200_b0", abi.COST_FD, {}), ("acrobot_T200_b1", abi.COST_FD, {}), ("acrobot_T200_b2", abi.COST_ANALYTIC, {}),
+    ("acrobot_T200_b3", abi.COST_ANALYTIC, {}), ("acrobot_lim15_T200_b1", abi.COST_FD, dict(u_min=[-1.5], u_max=[1.5])),
+    ("acrobot_lim15_T200_b2", abi.COST_ANALYTIC, dict(u_min=[-1.5], u_max=[1.5])), ("acrobot_cli_T499", abi.COST_FD, {}),
+])
+def test_acrobot_kernel_source_equals_oracle_bit_for_bit(golden_solver, case, cd, kw):
+    g = golden_solver
+    trips = lockstep(abi.MODEL_ACROBOT, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), True, cost_deriv=cd, **kw)
+    assert trips >= 10
+
+
+@pytest.mark.parametrize("libm", [True, False])
+@pytest.mark.parametrize("case,cd", [("integrator_cli_T99", abi.COST_FD), ("integrator_rand_T60_b0", abi.COST_FD),
+                                     ("integrator_rand_T60_b1", abi.COST_ANALYTIC), ("integrator_rand_T60_b2", abi.COST_FD)])
+def test_double_integrator_kernel_source_equals_oracle_bit_for_bit(golden_solver, case, cd, libm):
+    g = golden_solver
+    lockstep(abi.MODEL_DOUBLE_INTEGRATOR, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), libm,
+             goal=list(g[case + "/goal"]), cost_deriv=cd)
+
+
+def test_warm_start_kernel_source_equals_oracle():
+    rng = np.random.default_rng(3)
+    x0, u0 = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (90, 1))
+    o, e = O.OracleSolver(abi.MODEL_ACROBOT, 0.02), E.EmuSolver(abi.MODEL_ACROBOT, 0.02, libm=True)
+    o.init(x0, u0), e.init(x0, u0)
+    o.iterate(4), e.iterate(4)
+    assert o.warm_start(x0 + 0.02) == e.warm_start(x0 + 0.02)
+    o.iterate(3), e.iterate(3)
+    for f in ARR:
+        assert np.array_equal(o.get(f), e.get(f)), f
+
+
+def test_boxqp_paths_against_reference_golden(golden_leaf):
+    """Both boxQP code paths of the kernels (scalar m == 1, general m) against the reference's results."""
+    g = golden_leaf
+    for i in range(len(g["qp_m"])):
+        m = int(g["qp_m"][i])
+        args = (g["qp_Q"][i][:m, :m], g["qp_c"][i][:m], g["qp_x0"][i][:m], g["qp_lo"][i][:m], g["qp_hi"][i][:m])
+        ores, ox, ovf, oR = O.boxqp(*args)
+        for generic in ([False, True] if m == 1 else [True]):
+            res, x, vf, R = E.boxqp(*args, generic=generic)
+            assert res == ores == g["qp_result"][i]
+            assert np.array_equal(x, ox) and (vf == ovf).all()
+            assert np.allclose(x, g["qp_x"][i][:m], rtol=1e-12, atol=1e-14)
+            if res != 6:
+                assert np.array_equal(R, oR)
+
+
+def test_trig_noise_floor():
+    """How far the deterministic sincos moves an acrobot solve away from the libm oracle: this is the
+    floor under every GPU-vs-oracle tolerance in test_gpu_parity.py."""
+    import bench
+    B, T = 24, 200
+    x0, u0 = bench.synth_inputs_cpu(B, T, 12345)
+    errK = {1: [], 5: [], 20: []}
+    errc = []
+    for b in range(B):
+        o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC)
+        e = E.EmuSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC)
+        o.init(x0[b], u0[b]), e.init(x0[b], u0[b])
+        done = 0
+        for n in (1, 5, 20):
+            o.iterate(n - done), e.iterate(n - done)
+            done = n
+            errK[n].append(np.abs(o.get("K") - e.get("K")).max() / np.abs(o.get("K")).max())
+        o.iterate(200), e.iterate(200)
+        errc.append(abs(o.cost - e.cost) / abs(o.cost))
+    assert max(errK[1]) < 1e-8 and max(errK[5]) < 1e-7
+    assert np.mean(np.array(errK[20]) < 1e-6) >= 0.85
+    assert np.mean(np.array(errc) < 1e-6) >= 0.9
