@@ -46,6 +46,7 @@ struct KArgs {
   const S *x0;
   S *xs, *us, *K, *k, *Vx0, *Vxx0;
   TrajState<S> *st;
+  S *slotF, *slotC, *slotCandX, *slotCandU; /* per-warp work buffers, see SlotPtrs */
   unsigned long long *queue;
   long long B;
   int op;
@@ -67,10 +68,16 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) ilqr_warp_kernel(co
   const size_t per_warp = warp_smem_bytes<Sc, S>(a.P.T);
   unsigned char *mine = smem_raw + (threadIdx.x >> 5) * per_warp;
   Sc &sc = *reinterpret_cast<Sc *>(mine);
-  S *gterm = reinterpret_cast<S *>(mine + sizeof(Sc));
+  const int T = a.P.T;
+  const size_t slot = (size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  SlotPtrs<S> sl;
+  sl.F = a.slotF + slot * (size_t)T * (N + M) * N;
+  sl.C = a.slotC ? a.slotC + slot * (size_t)T * Sc::NC : nullptr;
+  sl.cand_x = a.slotCandX + slot * (size_t)a.P.n_alpha * T * N;
+  sl.cand_u = a.slotCandU + slot * (size_t)a.P.n_alpha * T * M;
+  sl.gterm = reinterpret_cast<S *>(mine + sizeof(Sc));
   WarpExec<N, M, S> ex;
   ex.lane = threadIdx.x & 31;
-  const int T = a.P.T;
   for (;;) {
     unsigned long long b = 0;
     if (ex.lane == 0) b = atomicAdd(a.queue, 1ULL);
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) ilqr_warp_kernel(co
     tr.Vx0 = a.Vx0 + b * N;
     tr.Vxx0 = a.Vxx0 + b * N * N;
     tr.st = a.st + b;
-    Core<Model, S, CD, WarpExec<N, M, S>> core(a.P, sc, gterm, ex, tr);
+    Core<Model, S, CD, WarpExec<N, M, S>> core(a.P, sc, ex, tr, sl);
     switch (a.op) {
       case kOpInit: core.op_init(); break;
       case kOpWarm: core.op_warm_start(); break;
@@ -134,6 +141,8 @@ struct ilqr_handle {
   cudaStream_t stream = nullptr;
   void *x0 = nullptr, *xs = nullptr, *us = nullptr, *K = nullptr, *k = nullptr, *Vx0 = nullptr, *Vxx0 = nullptr,
        *st = nullptr, *tmp = nullptr;
+  void *slotF = nullptr, *slotC = nullptr, *slotCandX = nullptr, *slotCandU = nullptr; /* per resident warp */
+  long long slots = 0;
   unsigned long long *queue = nullptr;
   int num_sms = 0;
   int64_t launches = 0;
@@ -195,6 +204,24 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
   long long want = (h->desc.B + kWarpsPerCta - 1) / kWarpsPerCta;
   long long cap = (long long)per_sm * h->num_sms;
   const int grid = (int)(want < cap ? want : cap);
+  /* the work buffers of the resident warps (Jacobian columns, FD cost derivatives, line-search candidates) */
+  const long long slots = (long long)grid * kWarpsPerCta;
+  if (slots > h->slots) {
+    CU(h, cudaStreamSynchronize(h->stream));
+    void **bufs[] = {&h->slotF, &h->slotC, &h->slotCandX, &h->slotCandU};
+    const size_t T = (size_t)h->desc.T, na = (size_t)h->desc.params.n_alpha;
+    const size_t per[] = {T * (N + M) * N, CD == kCostFD ? T * Scratch<N, M, S, CD>::NC : 0, na * T * N, na * T * M};
+    for (int i = 0; i < 4; i++) {
+      if (*bufs[i]) CU(h, cudaFree(*bufs[i]));
+      *bufs[i] = nullptr;
+      if (per[i]) CU(h, cudaMalloc(bufs[i], per[i] * sizeof(S) * (size_t)slots));
+    }
+    h->slots = slots;
+  }
+  a.slotF = (S *)h->slotF;
+  a.slotC = (S *)h->slotC;
+  a.slotCandX = (S *)h->slotCandX;
+  a.slotCandU = (S *)h->slotCandU;
   CU(h, cudaMemsetAsync(h->queue, 0, sizeof(unsigned long long), h->stream));
   kern<<<grid, kThreads, smem, h->stream>>>(a);
   CU(h, cudaGetLastError());
@@ -246,7 +273,8 @@ int ilqr_destroy(ilqr_handle *h) {
   {
     DeviceGuard g(h->desc.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *bufs[] = {h->x0, h->xs, h->us, h->K, h->k, h->Vx0, h->Vxx0, h->st, h->tmp, h->queue};
+    void *bufs[] = {h->x0, h->xs, h->us, h->K, h->k, h->Vx0, h->Vxx0, h->st, h->tmp, h->queue,
+                    h->slotF, h->slotC, h->slotCandX, h->slotCandU};
     for (void *b : bufs)
       if (b) cudaFree(b);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -2,50 +2,51 @@
  * ilqr_core.cuh — one iLQR problem instance, solved by ONE WARP.
  *
  * This is the whole hot path of the reference for one trajectory, re-designed for a 32-lane warp
- * that owns the trajectory from the first rollout to termination:
+ * that owns the trajectory from the first rollout to termination.  One loop trip
+ * (src/ilqr_core.cpp:103-288) is
  *
- *   backward pass (src/ilqr_core.cpp:350-401), serial in t, per timestep
- *     - lanes 0 .. 2(n+m)-1 evaluate the perturbed Euler steps of the central-difference
- *       Jacobians fx, fu (src/derivatives.cpp:15-26, include/finite_diff.h:35-47);
- *       the remaining lanes evaluate the cost stencils (src/derivatives.cpp:29-144,
- *       finite_diff.h:22-33,67-86) or the closed forms — derivatives are recomputed on the fly
- *       and never written to HBM;
- *     - the (n+m)^2 Q-function entries are spread one per lane (:359-367);
- *     - one lane runs the boxQP (src/boxqp.cpp) and the gains (:369-389);
- *     - the n + n^2 entries of Vx, Vxx are spread one per lane (:391-393);
- *     Vx/Vxx and every intermediate live in the warp's shared-memory scratch.
- *   line search (src/ilqr_core.cpp:184-226): the n_alpha candidate rollouts (:305-337) run
- *     concurrently, one per lane; the first accepted index is taken, which is result-identical
- *     to the reference's serial early-exit loop because every candidate starts from the same
- *     (xs, us, K, k);  the accepted candidate is then re-rolled to commit xs/us in place.
- *   outer loop, lambda schedule, termination (src/ilqr_core.cpp:103-288): per-trajectory scalars
- *     in the scratch; lambda/dlambda are per trajectory (process-wide statics in the reference).
+ *   1. derivative sweep — only when the trajectory changed (flgChange, :115-120).  The central
+ *      differences of the Euler step (src/derivatives.cpp:15-26, finite_diff.h:35-47) have no
+ *      dependence between timesteps, so they are NOT done inside the serial backward recursion:
+ *      the T*(n+m) (timestep, variable) pairs are spread over the 32 lanes, each lane evaluating
+ *      its +eps / -eps pair and writing one Jacobian column.  With finite-difference cost
+ *      derivatives (src/derivatives.cpp:29-144) the T*20 stencil outputs are spread the same way.
+ *      The columns go to a per-warp buffer that stays in L2 (acrobot, T = 200: 32 KB).
+ *   2. backward pass (:350-401), serial in t, five warp phases per timestep: F^T Vxx' entries one
+ *      per lane; the (n+m)^2 Q-function entries one per lane (:359-367); boxQP + gains on one lane
+ *      (src/boxqp.cpp, :369-389); the n + n^2 entries of Vx, Vxx one per lane (:391-392);
+ *      symmetrisation (:393) and the k / K / gradient-norm-term stores.  Vx, Vxx and every
+ *      intermediate live in the warp's shared-memory scratch.
+ *   3. line search (:184-226): the n_alpha candidate rollouts (:305-337) run concurrently, one per
+ *      lane, each streaming its states/controls to a per-warp candidate buffer; the first accepted
+ *      index is taken — result-identical to the reference's serial early-exit loop, because every
+ *      candidate starts from the same (xs, us, K, k) — and the accepted candidate is committed by
+ *      a coalesced copy (no re-roll).
+ *   4. lambda schedule / termination (:136-159, :242-282) on per-trajectory scalars; lambda and
+ *      dlambda are per trajectory here (process-wide statics in the reference, ilqr.h:17-18).
  *
- * HBM traffic is the minimum the algorithm allows: a backward pass reads xs, us and writes K, k;
- * the line search reads xs, us, K, k; a commit rewrites xs, us.  The per-trajectory arrays are
- * contiguous in t, moved in 32-timestep tiles by coalesced warp-wide copies.
+ * Per-trajectory arrays are contiguous in t and move in tiles by coalesced warp-wide copies.
  *
  * Lanes communicate only through the scratch (never shuffles), in phases separated by a warp
  * barrier.  That lets tests/emu/ compile this same header with g++ and run the phases lane by
- * lane on the CPU (`HostExec`), so the control flow and the arithmetic order can be checked
- * bit-for-bit against the oracle without a GPU.  The emulator is test infrastructure; the
- * product only ever instantiates `WarpExec`.
+ * lane on the CPU (`HostExec`), so control flow and arithmetic order are checked bit for bit
+ * against the oracle without a GPU.  The emulator is test infrastructure; the product only ever
+ * instantiates `WarpExec`.
  *
  * Arithmetic order follows the reference statement by statement (sequential accumulations from
- * zero, no FMA contraction: the .cu is built with -fmad=false) so that f64 results differ from
- * the reference only through sin/cos.
+ * zero, no FMA contraction: the .cu is built with -fmad=false), so f64 results differ from the
+ * reference only through sin/cos (trig.cuh).
  */
 #ifndef ILQR_CORE_CUH_
 #define ILQR_CORE_CUH_
-
-#include <type_traits>
 
 #include "boxqp.cuh"
 #include "models.cuh"
 
 namespace ilqr {
 
-constexpr int kTile = 32;      /* timesteps per staged tile */
+constexpr int kTile = 32;      /* timesteps per staged tile in the rollouts */
+constexpr int kTileB = 8;      /* timesteps per staged tile in the backward pass */
 constexpr int kMaxAlpha = 16;  /* ILQR_MAX_ALPHA */
 
 /* exit reasons / ops: numeric values equal the ILQR_* macros of include/ilqr_b200.h */
@@ -86,59 +87,34 @@ struct TrajPtrs {
   TrajState<S> *st;
 };
 
-/* the warp's working set */
-#if defined(__CUDACC__)
-#define ILQR_HDC __host__ __device__ constexpr
-#else
-#define ILQR_HDC constexpr
-#endif
-ILQR_HDC int popc_(unsigned v) { return v ? (int)(v & 1u) + popc_(v >> 1) : 0; }
-
-/* f(integral_constant<int, 0>) ... f(integral_constant<int, G-1>): loops whose index must be a
- * compile-time constant (so per-model tables fold to literals in device code) */
-template <int G, class F>
-ILQR_HD void static_for(F &&f) {
-  if constexpr (G > 0) {
-    static_for<G - 1>(f);
-    f(std::integral_constant<int, G - 1>{});
-  }
-}
-ILQR_HD int popcnt(unsigned v) {
-#if defined(__CUDA_ARCH__)
-  return __popc(v);
-#else
-  return __builtin_popcount(v);
-#endif
-}
-
-/* finite-difference variants of the model's trig arguments: argument g is needed at the base point
- * and at +-eps on each state variable it depends on */
-template <class Model>
-struct TrigVariants {
-  static constexpr int KT = Model::kTrig;
-  static ILQR_HDC int count(int g) { return 1 + 2 * popc_(Model::trig_deps(g)); }
-  static ILQR_HDC int offset(int g) { return g <= 0 ? 0 : offset(g - 1) + count(g - 1); }
-  static constexpr int total = offset(KT);
+/* per-WARP work buffers in global memory (one set per resident warp, reused across trajectories) */
+template <typename S>
+struct SlotPtrs {
+  S *F;      /* [T][n+m][n]   Jacobian columns of the Euler step: F[t][j][r] = d x'_r / d (x|u)_j   */
+  S *C;      /* [T][NC]       finite-difference cost derivatives (cx cu cxx cxu cuu), FD mode only  */
+  S *cand_x; /* [n_alpha][T][n]  candidate states x_1..x_T of the line search                       */
+  S *cand_u; /* [n_alpha][T][m]  candidate controls                                                  */
+  S *gterm;  /* [T] per-timestep terms of the gradient norm (shared memory on the device)           */
 };
 
-template <int N, int M, typename S, int NTV = 1, int KT = 1>
+/* the warp's working set */
+template <int N, int M, typename S, int CD>
 struct Scratch {
   static constexpr int NM = N + M;
-  /* staged tiles */
+  static constexpr int NC = N + M + N * N + N * M + M * M;
+  /* staged tiles: rollouts use kTile timesteps, the backward pass the first kTileB of the same arrays */
   S xs[kTile * N], us[kTile * M], K[kTile * M * N], k[kTile * M];
-  S xn[kTile * N], un[kTile * M];
+  S Ft[kTileB * NM * N];                     /* backward: Jacobian columns of the tile      */
+  S Ct[CD == kCostFD ? kTileB * NC : 1];     /* backward: FD cost derivatives of the tile   */
   /* one timestep */
   S x[N], u[M];
-  S E[2 * NM * N];      /* perturbed Euler steps: row 2j = +eps on variable j, 2j+1 = -eps */
-  S F[N * NM];          /* [fx | fu], N x (N+M) row-major */
-  S cx[N], cu[M], cxx[N * N], cxu[N * M], cuu[M * M];
+  S cx[N], cu[M], cxx[N * N], cxu[N * M], cuu[M * M]; /* terminal / analytic cost derivatives */
   S Vx[N], Vxx[N * N];  /* value function at i+1, overwritten with i at the end of the step */
   S W[NM * N];          /* F^T Vxx' */
   S Qx[N], Qu[M], Qxx[N * N], Qux[M * N], Quu[M * M];
   S Kc[M * N], kc[M], kprev[M];
   S Vtmp[N * N], Vxn[N];
   S newcost[kMaxAlpha];
-  S bsn[NTV > 0 ? NTV : 1], bcs[NTV > 0 ? NTV : 1];                   /* backward: sincos per (argument, FD variant) */
   QPWork<M, S> qp;
   TrajState<S> st;
   int flag;
@@ -149,7 +125,6 @@ struct LaneRegs {
   S x[N];
   S uc[M];
   S cost;
-  S gn;
 };
 
 #if defined(__CUDACC__)
@@ -175,37 +150,35 @@ struct HostExec {
   }
 };
 
+/* read that must see what another lane of this warp stored to global memory before the last barrier */
+template <typename S>
+ILQR_HD S ld_fresh(const S *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+
 template <class Model, typename S, int CD, class Exec>
 struct Core {
   static constexpr int N = Model::N, M = Model::M, NM = N + M;
-  static constexpr int KT = Model::kTrig;
-  using TV = TrigVariants<Model>;
-  using Sc = Scratch<N, M, S, TV::total, KT>;
+  using Sc = Scratch<N, M, S, CD>;
   using Lane = LaneRegs<N, M, S>;
+  static constexpr int NC = Sc::NC;
 
   const SolveParams<S> &P;
   Sc &sc;
   Exec &ex;
   TrajPtrs<S> tr;
-  S *gterm; /* [T] per-timestep terms of the gradient norm, in the warp's shared memory after the scratch */
+  SlotPtrs<S> sl;
 
-  ILQR_HD Core(const SolveParams<S> &p, Sc &s, S *g, Exec &e, const TrajPtrs<S> &t) : P(p), sc(s), ex(e), tr(t), gterm(g) {}
+  ILQR_HD Core(const SolveParams<S> &p, Sc &s, Exec &e, const TrajPtrs<S> &t, const SlotPtrs<S> &w)
+      : P(p), sc(s), ex(e), tr(t), sl(w) {}
 
-  /* ---- tiles ---------------------------------------------------------------------------- */
-  ILQR_HD void copy_in(S *dst, const S *src, int count) {
-    ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < count; e += 32) dst[e] = src[e];
-    });
-  }
-  ILQR_HD void copy_out(S *dst, const S *src, int count) {
-    ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < count; e += 32) dst[e] = src[e];
-    });
-  }
+  /* ---- finite differences ------------------------------------------------------------------ */
 
-  /* ---- derivatives ---------------------------------------------------------------------- */
-
-  /* perturbed copy helpers: v[q] (+ sa*eps if q == a) (+ sb*eps if q == b), in that order */
+  /* perturbed copy: v[q] (+ da if q == a) (+ db if q == b), in that order */
   template <int D>
   ILQR_HD static void perturb(const S *v, int a, S da, int b, S db, S *out) {
 #pragma unroll
@@ -217,7 +190,7 @@ struct Core {
     }
   }
 
-  /* One finite-difference cost-stencil output (src/derivatives.cpp:29-144).  Output ids:
+  /* One finite-difference cost-stencil output (src/derivatives.cpp:29-144) at (x, u).  Output ids:
    * [0,N) cx, [N,N+M) cu, then cxx upper triangle (i <= j, row by row), cuu upper triangle,
    * then cxu (i, j).  terminal: cx and cxx of final_cost only. */
   static constexpr int kNxx = N * (N + 1) / 2, kNuu = M * (M + 1) / 2;
@@ -235,27 +208,27 @@ struct Core {
     j = i + o;
   }
 
-  ILQR_HD void cost_stencil(int o, bool terminal) {
+  ILQR_HD void cost_stencil(int o, bool terminal, const S *x, const S *u, S *cx, S *cu, S *cxx, S *cxu, S *cuu) {
     const S eps = P.fd_eps;
     const S *mp = P.mp;
     S xa[N], ua[M];
     auto fx = [&](const S *xv, const S *uv) -> S { return terminal ? Model::final_cost(xv, mp) : Model::cost(xv, uv, mp); };
     if (o < N) { /* finite_diff_gradient wrt x, finite_diff.h:22-33 */
-      perturb<N>(sc.x, o, eps, -1, S(0), xa);
-      const S p = fx(xa, sc.u);
-      perturb<N>(sc.x, o, -eps, -1, S(0), xa);
-      const S m = fx(xa, sc.u);
-      sc.cx[o] = (p - m) / (2 * eps);
+      perturb<N>(x, o, eps, -1, S(0), xa);
+      const S p = fx(xa, u);
+      perturb<N>(x, o, -eps, -1, S(0), xa);
+      const S m = fx(xa, u);
+      cx[o] = (p - m) / (2 * eps);
       return;
     }
     o -= N;
     if (!terminal) {
       if (o < M) {
-        perturb<M>(sc.u, o, eps, -1, S(0), ua);
-        const S p = Model::cost(sc.x, ua, mp);
-        perturb<M>(sc.u, o, -eps, -1, S(0), ua);
-        const S m = Model::cost(sc.x, ua, mp);
-        sc.cu[o] = (p - m) / (2 * eps);
+        perturb<M>(u, o, eps, -1, S(0), ua);
+        const S p = Model::cost(x, ua, mp);
+        perturb<M>(u, o, -eps, -1, S(0), ua);
+        const S m = Model::cost(x, ua, mp);
+        cu[o] = (p - m) / (2 * eps);
         return;
       }
       o -= M;
@@ -263,17 +236,17 @@ struct Core {
     if (o < kNxx) { /* finite_diff_hessian wrt x, finite_diff.h:67-86 */
       int i, j;
       tri_index(o, N, i, j);
-      perturb<N>(sc.x, i, eps, j, eps, xa);
-      const S pp = fx(xa, sc.u);
-      perturb<N>(sc.x, i, -eps, j, eps, xa);
-      const S mpv = fx(xa, sc.u);
-      perturb<N>(sc.x, i, eps, j, -eps, xa);
-      const S pm = fx(xa, sc.u);
-      perturb<N>(sc.x, i, -eps, j, -eps, xa);
-      const S mm = fx(xa, sc.u);
+      perturb<N>(x, i, eps, j, eps, xa);
+      const S pp = fx(xa, u);
+      perturb<N>(x, i, -eps, j, eps, xa);
+      const S mpv = fx(xa, u);
+      perturb<N>(x, i, eps, j, -eps, xa);
+      const S pm = fx(xa, u);
+      perturb<N>(x, i, -eps, j, -eps, xa);
+      const S mm = fx(xa, u);
       const S v = (pp - mpv - pm + mm) / (4 * eps * eps);
-      sc.cxx[i * N + j] = v;
-      sc.cxx[j * N + i] = v;
+      cxx[i * N + j] = v;
+      cxx[j * N + i] = v;
       return;
     }
     o -= kNxx;
@@ -281,114 +254,83 @@ struct Core {
     if (o < kNuu) {
       int i, j;
       tri_index(o, M, i, j);
-      perturb<M>(sc.u, i, eps, j, eps, ua);
-      const S pp = Model::cost(sc.x, ua, mp);
-      perturb<M>(sc.u, i, -eps, j, eps, ua);
-      const S mpv = Model::cost(sc.x, ua, mp);
-      perturb<M>(sc.u, i, eps, j, -eps, ua);
-      const S pm = Model::cost(sc.x, ua, mp);
-      perturb<M>(sc.u, i, -eps, j, -eps, ua);
-      const S mm = Model::cost(sc.x, ua, mp);
+      perturb<M>(u, i, eps, j, eps, ua);
+      const S pp = Model::cost(x, ua, mp);
+      perturb<M>(u, i, -eps, j, eps, ua);
+      const S mpv = Model::cost(x, ua, mp);
+      perturb<M>(u, i, eps, j, -eps, ua);
+      const S pm = Model::cost(x, ua, mp);
+      perturb<M>(u, i, -eps, j, -eps, ua);
+      const S mm = Model::cost(x, ua, mp);
       const S v = (pp - mpv - pm + mm) / (4 * eps * eps);
-      sc.cuu[i * M + j] = v;
-      sc.cuu[j * M + i] = v;
+      cuu[i * M + j] = v;
+      cuu[j * M + i] = v;
       return;
     }
     o -= kNuu;
     if (o < N * M) { /* calculate_cxu, src/derivatives.cpp:114-144 (its own stencil) */
       const int i = o / M, j = o % M;
       S xp[N], xm[N], up[M], um[M];
-      perturb<N>(sc.x, i, eps, -1, S(0), xp);
-      perturb<N>(sc.x, i, -eps, -1, S(0), xm);
-      perturb<M>(sc.u, j, eps, -1, S(0), up);
-      perturb<M>(sc.u, j, -eps, -1, S(0), um);
-      sc.cxu[i * M + j] =
+      perturb<N>(x, i, eps, -1, S(0), xp);
+      perturb<N>(x, i, -eps, -1, S(0), xm);
+      perturb<M>(u, j, eps, -1, S(0), up);
+      perturb<M>(u, j, -eps, -1, S(0), um);
+      cxu[i * M + j] =
           (Model::cost(xp, up, mp) - Model::cost(xm, up, mp) - Model::cost(xp, um, mp) + Model::cost(xm, um, mp)) /
           (4 * (eps * eps));
     }
   }
 
-  /* Phase: derivatives of timestep i at (sc.x, sc.u) -> sc.E (perturbed steps), sc.c*.
-   * Two sub-phases when the model has trig arguments: every (argument, variant) sincos on its own
-   * lane (the cost derivatives ride along on the lanes after those), then the 2(n+m) perturbed
-   * Euler steps from the tabulated values. */
-  ILQR_HD void phase_derivatives() {
-    constexpr int nDyn = 2 * NM;
-    constexpr int nCost = (CD == kCostFD) ? kStencilStep : 1;
-    constexpr int nTrig = TV::total;
-    ex.lanes([&](int lane, Lane &) {
-      for (int task = lane; task < nTrig + nCost; task += 32) {
-        if (KT > 0 && task < nTrig) {
-          if constexpr (KT > 0) {
-          int g = 0, off = 0;
-          unsigned deps = 0;
-          static_for<KT>([&](auto gc) {
-            constexpr int G = decltype(gc)::value;
-            constexpr int o = TV::offset(G);
-            constexpr unsigned dd = Model::trig_deps(G);
-            if (task >= o) {
-              g = G;
-              off = o;
-              deps = dd;
-            }
-          });
-          const int v = task - off;
-          int var = -1;
-          S d = 0;
-          if (v > 0) {
-            int rank = (v - 1) >> 1, seen = 0;
+  /* get_dynamics_derivatives (+ get_cost_derivatives / get_cost_2nd_derivatives in FD mode) for the
+   * whole horizon, parallel over (timestep, variable): lane <- task, each task the +eps / -eps pair
+   * of finite_diff_jacobian (finite_diff.h:35-47) for one column. */
+  ILQR_HD void derivative_sweep() {
+    const int T = P.T;
+    const int n_dyn = T * NM;
+    for (int base = 0; base < n_dyn; base += 32) {
+      ex.lanes([&](int lane, Lane &) {
+        const int task = base + lane;
+        if (task >= n_dyn) return;
+        const int t = task / NM, j = task - t * NM;
+        S x[N], u[M], xa[N], ua[M], fp[N], fm[N];
 #pragma unroll
-            for (int q = 0; q < N; q++)
-              if ((deps >> q) & 1u) {
-                if (seen == rank) var = q;
-                seen++;
-              }
-            d = ((v - 1) & 1) ? -P.fd_eps : P.fd_eps;
-          }
-          S xa[N];
-          perturb<N>(sc.x, var, d, -1, S(0), xa);
-          sincos_det(Model::trig_arg(g, xa), &sc.bsn[task], &sc.bcs[task]);
-          }
-        } else if (CD == kCostFD) {
-          cost_stencil(task - nTrig, false);
-        } else {
-          Model::cost_derivs(sc.x, sc.u, P.mp, false, sc.cx, sc.cu, sc.cxx, sc.cxu, sc.cuu);
-        }
-      }
-    });
-    ex.lanes([&](int lane, Lane &) {
-      for (int task = lane; task < nDyn; task += 32) { /* finite_diff_jacobian of integrate_dynamics, finite_diff.h:35-47 */
-        const int var = task >> 1, neg = task & 1;
-        const S d = neg ? -P.fd_eps : P.fd_eps;
-        S xa[N], ua[M], x1[N];
-        perturb<N>(sc.x, var, d, -1, S(0), xa);
-        perturb<M>(sc.u, var - N, d, -1, S(0), ua);
-        if constexpr (KT > 0) {
-          S sn[KT], cs[KT];
-          static_for<KT>([&](auto gc) { /* variant 0 = base value when the argument does not depend on `var` */
-            constexpr int G = decltype(gc)::value;
-            constexpr int o = TV::offset(G);
-            constexpr unsigned dd = Model::trig_deps(G);
-            int variant = 0;
-            if (var < N && ((dd >> var) & 1u)) variant = 1 + 2 * popcnt(dd & ((1u << var) - 1u)) + neg;
-            sn[G] = sc.bsn[o + variant];
-            cs[G] = sc.bcs[o + variant];
-          });
-          integrate_trig<Model, S>(xa, ua, P.mp, P.dt, sn, cs, x1);
-        } else {
-          integrate<Model, S>(xa, ua, P.mp, P.dt, x1);
-        }
+        for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
 #pragma unroll
-        for (int r = 0; r < N; r++) sc.E[task * N + r] = x1[r];
+        for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
+        perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
+        perturb<M>(u, j - N, P.fd_eps, -1, S(0), ua);
+        integrate<Model, S>(xa, ua, P.mp, P.dt, fp);
+        perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
+        perturb<M>(u, j - N, -P.fd_eps, -1, S(0), ua);
+        integrate<Model, S>(xa, ua, P.mp, P.dt, fm);
+#pragma unroll
+        for (int r = 0; r < N; r++) sl.F[(size_t)task * N + r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+      });
+    }
+    if constexpr (CD == kCostFD) {
+      const int n_c = T * kStencilStep;
+      for (int base = 0; base < n_c; base += 32) {
+        ex.lanes([&](int lane, Lane &) {
+          const int task = base + lane;
+          if (task >= n_c) return;
+          const int t = task / kStencilStep, o = task - t * kStencilStep;
+          S x[N], u[M];
+#pragma unroll
+          for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
+#pragma unroll
+          for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
+          S *c = sl.C + (size_t)t * NC;
+          cost_stencil(o, false, x, u, c, c + N, c + N + M, c + N + M + N * N, c + N + M + N * N + N * M);
+        });
       }
-    });
+    }
   }
 
   /* Vx[T] = cx[T], Vxx[T] = cxx[T]  (src/ilqr_core.cpp:353-354) from sc.x = xs[T] */
   ILQR_HD void phase_terminal() {
     ex.lanes([&](int lane, Lane &) {
       if (CD == kCostFD) {
-        for (int o = lane; o < kStencilTerm; o += 32) cost_stencil(o, true);
+        for (int o = lane; o < kStencilTerm; o += 32) cost_stencil(o, true, sc.x, sc.u, sc.cx, sc.cu, sc.cxx, sc.cxu, sc.cuu);
       } else if (lane == 0) {
         S cu[M], cxu[N * M], cuu[M * M];
         Model::cost_derivs(sc.x, sc.u, P.mp, true, sc.cx, cu, sc.cxx, cxu, cuu);
@@ -404,59 +346,67 @@ struct Core {
 
   /* ---- backward pass -------------------------------------------------------------------- */
 
-  /* One timestep of the backward recursion at (sc.x, sc.u) = (xs[i], us[i]); returns false when
-   * the boxQP reports failure (result < 1, src/ilqr_core.cpp:371).  On success sc.kc / sc.Kc hold
-   * k_i / K_i and sc.Vx / sc.Vxx the value function at i. */
-  ILQR_HD bool backward_step(S lam) {
-    phase_derivatives();
-    /* F = [fx | fu] column j = (f(+eps e_j) - f(-eps e_j)) / (2 eps) */
+  /* One timestep of the backward recursion for tile entry tt; returns false when the boxQP reports
+   * failure (result < 1, src/ilqr_core.cpp:371).  On success sc.kc / sc.Kc hold k_i / K_i and
+   * sc.Vx / sc.Vxx the value function at i. */
+  ILQR_HD bool backward_step(int tt, S lam) {
+    const S *F = sc.Ft + tt * NM * N; /* F[j][r]: column j of [fx | fu] */
+    const S *ut = sc.us + tt * M;
+    const S *cx, *cu, *cxx, *cxu, *cuu;
+    if constexpr (CD == kCostFD) {
+      cx = sc.Ct + tt * NC;
+      cu = cx + N;
+      cxx = cu + M;
+      cxu = cxx + N * N;
+      cuu = cxu + N * M;
+    } else {
+      cx = sc.cx;
+      cu = sc.cu;
+      cxx = sc.cxx;
+      cxu = sc.cxu;
+      cuu = sc.cuu;
+    }
+    /* W = F^T Vxx'  (the inner product of :361-363); closed-form cost derivatives ride on the last lane */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * NM; e += 32) {
-        const int r = e / NM, j = e % NM;
-        sc.F[e] = (sc.E[(2 * j) * N + r] - sc.E[(2 * j + 1) * N + r]) / (2 * P.fd_eps);
-      }
-    });
-    /* W = F^T Vxx' ; Qx = cx + fx^T Vx' ; Qu = cu + fu^T Vx'   (:359-360) */
-    ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < NM * N + NM; e += 32) {
-        if (e < NM * N) {
-          const int c = e / N, b = e % N;
-          S acc = 0;
+      for (int e = lane; e < NM * N; e += 32) {
+        const int c = e / N, b = e % N;
+        S acc = 0;
 #pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.F[r * NM + c] * sc.Vxx[r * N + b];
-          sc.W[e] = acc;
-        } else {
-          const int c = e - NM * N;
-          S acc = 0;
-#pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.F[r * NM + c] * sc.Vx[r];
-          if (c < N) sc.Qx[c] = sc.cx[c] + acc;
-          else sc.Qu[c - N] = sc.cu[c - N] + acc;
-        }
+        for (int r = 0; r < N; r++) acc += F[c * N + r] * sc.Vxx[r * N + b];
+        sc.W[e] = acc;
       }
+      if (CD == kCostAnalytic && lane == 31)
+        Model::cost_derivs(sc.xs + tt * N, ut, P.mp, false, sc.cx, sc.cu, sc.cxx, sc.cxu, sc.cuu);
     });
-    /* Qxx, Qux, Quu and the regularised QuuF (:361-367); QuuF goes straight into the QP */
+    /* Qx, Qu (:359-360), Qxx, Qux, Quu and the regularised QuuF (:361-367); QuuF goes straight into the QP */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + M * N + M * M; e += 32) {
+      for (int e = lane; e < N * N + M * N + M * M + NM; e += 32) {
         if (e < N * N) {
           const int a = e / N, b = e % N;
           S acc = 0;
 #pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.W[a * N + r] * sc.F[r * NM + b];
-          sc.Qxx[e] = sc.cxx[e] + acc;
+          for (int r = 0; r < N; r++) acc += sc.W[a * N + r] * F[b * N + r];
+          sc.Qxx[e] = cxx[e] + acc;
         } else if (e < N * N + M * N) {
           const int q = e - N * N, a = q / N, b = q % N;
           S acc = 0;
 #pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.W[(N + a) * N + r] * sc.F[r * NM + b];
-          sc.Qux[q] = sc.cxu[b * M + a] + acc;
-        } else {
+          for (int r = 0; r < N; r++) acc += sc.W[(N + a) * N + r] * F[b * N + r];
+          sc.Qux[q] = cxu[b * M + a] + acc;
+        } else if (e < N * N + M * N + M * M) {
           const int q = e - N * N - M * N, a = q / M, b = q % M;
           S acc = 0;
 #pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.W[(N + a) * N + r] * sc.F[r * NM + N + b];
-          sc.Quu[q] = sc.cuu[q] + acc;
-          sc.qp.Q[q] = (sc.cuu[q] + (a == b ? lam : S(0))) + acc;
+          for (int r = 0; r < N; r++) acc += sc.W[(N + a) * N + r] * F[(N + b) * N + r];
+          sc.Quu[q] = cuu[q] + acc;
+          sc.qp.Q[q] = (cuu[q] + (a == b ? lam : S(0))) + acc;
+        } else {
+          const int c = e - N * N - M * N - M * M;
+          S acc = 0;
+#pragma unroll
+          for (int r = 0; r < N; r++) acc += F[c * N + r] * sc.Vx[r];
+          if (c < N) sc.Qx[c] = cx[c] + acc;
+          else sc.Qu[c - N] = cu[c - N] + acc;
         }
       }
     });
@@ -468,8 +418,8 @@ struct Core {
       for (int j = 0; j < M; j++) {
         w.c[j] = sc.Qu[j];
         w.x0[j] = sc.kprev[j];
-        w.lo[j] = P.u_min[j] - sc.u[j];
-        w.hi[j] = P.u_max[j] - sc.u[j];
+        w.lo[j] = P.u_min[j] - ut[j];
+        w.hi[j] = P.u_max[j] - ut[j];
       }
       box_qp<M, S>(P.qp, w);
       if (w.result < 1) return;
@@ -547,16 +497,23 @@ struct Core {
         }
       }
     });
-    /* symmetrise (:393), roll the value function, remember k for the next warm start */
+    /* symmetrise (:393), roll the value function, remember k for the next warm start, stage k / K
+     * (:396-397) and the gradient-norm term of this timestep (:405-412) */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + N + M; e += 32) {
+      for (int e = lane; e < N * N + N + M + M * N + M + 1; e += 32) {
         if (e < N * N) {
           const int a = e / N, b = e % N;
           sc.Vxx[e] = S(0.5) * (sc.Vtmp[a * N + b] + sc.Vtmp[b * N + a]);
         } else if (e < N * N + N) {
           sc.Vx[e - N * N] = sc.Vxn[e - N * N];
-        } else {
+        } else if (e < N * N + N + M) {
           sc.kprev[e - N * N - N] = sc.kc[e - N * N - N];
+        } else if (e < N * N + N + M + M * N) {
+          sc.K[tt * M * N + e - (N * N + N + M)] = sc.Kc[e - (N * N + N + M)];
+        } else if (e < N * N + N + M + M * N + M) {
+          sc.k[tt * M + e - (N * N + N + M + M * N)] = sc.kc[e - (N * N + N + M + M * N)];
+        } else {
+          sl.gterm[tt] = gn_term(sc.kc, ut); /* caller offsets sl.gterm to the tile */
         }
       }
     });
@@ -566,8 +523,9 @@ struct Core {
   /* iLQR::backward_pass.  Returns the failing timestep or 0 (:371,400). */
   ILQR_HD int backward_pass(S lam) {
     const int T = P.T;
-    copy_in(sc.x, tr.xs + T * N, N);
+    S *const gterm_base = sl.gterm;
     ex.lanes([&](int lane, Lane &) {
+      if (lane < N) sc.x[lane] = tr.xs[T * N + lane];
       if (lane < M) {
         sc.u[lane] = 0;
         sc.kprev[lane] = tr.k[(T - 1) * M + lane]; /* :369 warm start of i = T-1: the previous pass's k[T-1] */
@@ -579,40 +537,34 @@ struct Core {
       }
     });
     phase_terminal();
-    for (int ti = (T - 1) / kTile; ti >= 0; ti--) {
-      const int t0 = ti * kTile;
-      const int cnt = (T - t0 < kTile) ? T - t0 : kTile;
+    int diverged_at = -1;
+    for (int ti = (T - 1) / kTileB; ti >= 0 && diverged_at < 0; ti--) {
+      const int t0 = ti * kTileB;
+      const int cnt = (T - t0 < kTileB) ? T - t0 : kTileB;
       ex.lanes([&](int lane, Lane &) {
         for (int e = lane; e < cnt * N; e += 32) sc.xs[e] = tr.xs[t0 * N + e];
         for (int e = lane; e < cnt * M; e += 32) sc.us[e] = tr.us[t0 * M + e];
-      });
-      for (int tt = cnt - 1; tt >= 0; tt--) {
-        ex.lanes([&](int lane, Lane &) {
-          if (lane < N) sc.x[lane] = sc.xs[tt * N + lane];
-          else if (lane < NM) sc.u[lane - N] = sc.us[tt * M + lane - N];
-        });
-        const bool ok = backward_step(lam);
-        if (!ok) { /* the steps above this one have already written their k, K (:396-397) */
-          const int done0 = tt + 1;
-          ex.lanes([&](int lane, Lane &) {
-            for (int e = lane + done0 * M * N; e < cnt * M * N; e += 32) tr.K[t0 * M * N + e] = sc.K[e];
-            for (int e = lane + done0 * M; e < cnt * M; e += 32) tr.k[t0 * M + e] = sc.k[e];
-          });
-          return t0 + tt;
+        for (int e = lane; e < cnt * NM * N; e += 32) sc.Ft[e] = ld_fresh(sl.F + (size_t)t0 * NM * N + e);
+        if constexpr (CD == kCostFD) {
+          for (int e = lane; e < cnt * NC; e += 32) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NC + e);
         }
-        ex.lanes([&](int lane, Lane &) {
-          for (int e = lane; e < M * N + M + 1; e += 32) {
-            if (e < M * N) sc.K[tt * M * N + e] = sc.Kc[e];
-            else if (e < M * N + M) sc.k[tt * M + e - M * N] = sc.kc[e - M * N];
-            else gterm[t0 + tt] = gn_term(sc.kc, sc.u);
-          }
-        });
+      });
+      sl.gterm = gterm_base + t0;
+      int first_done = 0; /* tile entries [first_done, cnt) hold finished k / K */
+      for (int tt = cnt - 1; tt >= 0; tt--) {
+        if (!backward_step(tt, lam)) { /* the steps above this one have already written their k, K (:396-397) */
+          diverged_at = t0 + tt;
+          first_done = tt + 1;
+          break;
+        }
       }
       ex.lanes([&](int lane, Lane &) {
-        for (int e = lane; e < cnt * M * N; e += 32) tr.K[t0 * M * N + e] = sc.K[e];
-        for (int e = lane; e < cnt * M; e += 32) tr.k[t0 * M + e] = sc.k[e];
+        for (int e = lane + first_done * M * N; e < cnt * M * N; e += 32) tr.K[t0 * M * N + e] = sc.K[e];
+        for (int e = lane + first_done * M; e < cnt * M; e += 32) tr.k[t0 * M + e] = sc.k[e];
       });
     }
+    sl.gterm = gterm_base;
+    if (diverged_at >= 0) return diverged_at;
     /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
     ex.lanes([&](int lane, Lane &) {
       for (int e = lane; e < N * N + N; e += 32) {
@@ -623,24 +575,24 @@ struct Core {
     return 0;
   }
 
-  /* get_gradient_norm (:405-412) as its own ascending loop; the solve loop gets the same number
-   * for free from the line-search rollout. */
-  ILQR_HD void gradient_norm_only() {
-    const int T = P.T;
-    ex.lanes([&](int lane, Lane &L) {
-      if (lane != 0) return;
-      S acc = 0;
-      for (int t = 0; t < T; t++) acc += gn_term(tr.k + t * M, tr.us + t * M);
-      sc.st.gnorm = acc / T;
-    });
-  }
-  /* the same number from the terms the backward pass just left in gterm (ascending t, like the reference) */
+  /* get_gradient_norm (:405-412): mean_t max_j |k_tj| / (|u_tj| + 1), summed in ascending t like the
+   * reference, from the terms the backward pass left in gterm ... */
   ILQR_HD void gradient_norm_from_terms() {
     const int T = P.T;
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
       S acc = 0;
-      for (int t = 0; t < T; t++) acc += gterm[t];
+      for (int t = 0; t < T; t++) acc += sl.gterm[t];
+      sc.st.gnorm = acc / T;
+    });
+  }
+  /* ... or from k and us in global memory (after a pass that stopped early) */
+  ILQR_HD void gradient_norm_only() {
+    const int T = P.T;
+    ex.lanes([&](int lane, Lane &) {
+      if (lane != 0) return;
+      S acc = 0;
+      for (int t = 0; t < T; t++) acc += gn_term(tr.k + t * M, tr.us + t * M);
       sc.st.gnorm = acc / T;
     });
   }
@@ -688,7 +640,8 @@ struct Core {
     });
   }
 
-  /* The candidate rollouts of the line search, lane a <-> alpha[a]; costs land in sc.newcost. */
+  /* The candidate rollouts of the line search, lane a <-> alpha[a]: costs land in sc.newcost, the
+   * candidate's controls and states stream to the warp's candidate buffer. */
   ILQR_HD void rollout_candidates() {
     const int T = P.T;
     const int na = P.n_alpha;
@@ -703,8 +656,15 @@ struct Core {
       ex.lanes([&](int lane, Lane &L) {
         if (lane >= na) return;
         const S alpha = P.alpha[lane];
-        for (int tt = 0; tt < cnt; tt++)
+        S *cx = sl.cand_x + ((size_t)lane * T + t0) * N;
+        S *cu = sl.cand_u + ((size_t)lane * T + t0) * M;
+        for (int tt = 0; tt < cnt; tt++) {
           rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, kRollClosed);
+#pragma unroll
+          for (int j = 0; j < M; j++) cu[tt * M + j] = L.uc[j];
+#pragma unroll
+          for (int i = 0; i < N; i++) cx[tt * N + i] = L.x[i];
+        }
       });
     }
     ex.lanes([&](int lane, Lane &L) {
@@ -714,8 +674,20 @@ struct Core {
     });
   }
 
-  /* One rollout that commits xs, us in place (what forward_pass does to the member arrays,
-   * :323,334); returns the cost in sc.st.new_cost. */
+  /* accept candidate a: xs[1..T], us[0..T-1] <- its rollout (what forward_pass left in the member
+   * arrays, :323,334); xs[0] = x0 already */
+  ILQR_HD void commit_candidate(int a) {
+    const int T = P.T;
+    ex.lanes([&](int lane, Lane &) {
+      const S *cx = sl.cand_x + (size_t)a * T * N;
+      const S *cu = sl.cand_u + (size_t)a * T * M;
+      for (int e = lane; e < T * N; e += 32) tr.xs[N + e] = ld_fresh(cx + e);
+      for (int e = lane; e < T * M; e += 32) tr.us[e] = ld_fresh(cu + e);
+    });
+  }
+
+  /* One rollout on lane 0 that rewrites xs, us in place (init_traj, warm start, test hook); the
+   * cost is returned in sc.st.new_cost. */
   ILQR_HD void rollout_commit(S alpha, int mode) {
     const int T = P.T;
     ex.lanes([&](int lane, Lane &L) {
@@ -731,15 +703,11 @@ struct Core {
         if (lane != 0) return;
         for (int tt = 0; tt < cnt; tt++) {
 #pragma unroll
-          for (int i = 0; i < N; i++) sc.xn[tt * N + i] = L.x[i];
+          for (int i = 0; i < N; i++) tr.xs[(t0 + tt) * N + i] = L.x[i];
           rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, mode);
 #pragma unroll
-          for (int j = 0; j < M; j++) sc.un[tt * M + j] = L.uc[j];
+          for (int j = 0; j < M; j++) tr.us[(t0 + tt) * M + j] = L.uc[j];
         }
-      });
-      ex.lanes([&](int lane, Lane &) {
-        for (int e = lane; e < cnt * N; e += 32) tr.xs[t0 * N + e] = sc.xn[e];
-        for (int e = lane; e < cnt * M; e += 32) tr.us[t0 * M + e] = sc.un[e];
       });
     }
     ex.lanes([&](int lane, Lane &L) {
@@ -806,6 +774,7 @@ struct Core {
 
   ILQR_HD void op_backward_once(S lam) {
     load_state();
+    derivative_sweep();
     const int d = backward_pass(lam);
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
@@ -830,10 +799,14 @@ struct Core {
   ILQR_HD void op_iterate(int n_iters) {
     load_state();
     int done_here = 0;
+    bool have_derivs = false; /* the warp's F / C buffers hold this trajectory's current derivatives */
     while (sc.st.iter < P.max_iter && done_here < n_iters && sc.st.status == kRunning) {
       done_here++;
-      /* derivatives are recomputed inside every backward pass, so flgChange (:115-120) only
-       * feeds the sweep counter */
+      /* :115-120 */
+      if (sc.st.flg_change || !have_derivs) {
+        derivative_sweep();
+        have_derivs = true;
+      }
       ex.lanes([&](int lane, Lane &) {
         if (lane != 0) return;
         sc.st.trips++;
@@ -864,22 +837,24 @@ struct Core {
         }
         back_done = true;
       }
-      if (back_done) {
-        gradient_norm_from_terms();
-        rollout_candidates();
-      } else {
-        gradient_norm_only();
-      }
-      /* :153-159, then the acceptance test :199-213 in the reference's serial order */
+      if (back_done) gradient_norm_from_terms();
+      else gradient_norm_only();
+      /* :153-159 */
+      ex.lanes([&](int lane, Lane &) {
+        if (lane != 0) return;
+        sc.flag = 0;
+        if (sc.st.gnorm < P.tol_grad && sc.st.lam < P.grad_lambda_gate) {
+          sc.st.status = kExitGrad;
+          sc.flag = 2;
+        }
+      });
+      if (sc.flag == 2) break; /* gradient exit: `break` before iter++ */
+      if (back_done) rollout_candidates();
+      /* the acceptance test :199-213 in the reference's serial order */
       ex.lanes([&](int lane, Lane &) {
         if (lane != 0) return;
         TrajState<S> &s = sc.st;
         sc.flag = 0;
-        if (s.gnorm < P.tol_grad && s.lam < P.grad_lambda_gate) {
-          s.status = kExitGrad;
-          sc.flag = 2;
-          return;
-        }
         s.alpha_index = -1;
         S alpha = 0;
         if (back_done) {
@@ -902,9 +877,8 @@ struct Core {
         }
         s.alpha = alpha;
       });
-      if (sc.flag == 2) break; /* gradient exit: `break` before iter++ */
       const bool fwd_done = sc.flag == 1;
-      if (fwd_done) rollout_commit(sc.st.alpha, kRollClosed);
+      if (fwd_done) commit_candidate(sc.st.alpha_index);
       ex.lanes([&](int lane, Lane &) {
         if (lane != 0) return;
         TrajState<S> &s = sc.st;
@@ -912,7 +886,7 @@ struct Core {
         if (fwd_done) { /* :242-263 */
           s.dlam = fmin_(s.dlam / P.lambda_factor, 1 / P.lambda_factor);
           s.lam = s.lam * s.dlam * S(s.lam > P.lambda_min);
-          s.cost = sc.newcost[s.alpha_index];
+          s.cost = s.new_cost;
           s.flg_change = 1;
           s.n_accept++;
           if (s.dcost < P.tol_fun) {

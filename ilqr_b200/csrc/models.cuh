@@ -31,15 +31,6 @@ ILQR_HD double t_abs(double v) { return ::fabs(v); }
 ILQR_HD float t_sqrt(float v) { return ::sqrtf(v); }
 ILQR_HD float t_abs(float v) { return ::fabsf(v); }
 
-/*
- * Trig protocol.  A model whose dynamics needs sin/cos declares the kTrig ARGUMENTS it takes them
- * of (`trig_arg`) and which state variables each argument depends on (`trig_deps`, a bit mask), and
- * evaluates its dynamics from the values handed in (`dynamics_trig`).  The solver then spreads the
- * sincos evaluations of a timestep over the lanes of the warp — one lane per (argument, finite-
- * difference variant) in the backward pass, one per (line-search candidate, argument) in the
- * rollouts — instead of having one lane grind through all of them.  kTrig == 0: plain `dynamics`.
- */
-
 /* ------------------------------------------------------------------------------------------
  * Acrobot — include/acrobot.h.  n = 4 (q1, q2, q1dot, q2dot), m = 1 (elbow torque) :27-28.
  * mp[0..3] = goal, set to (3.1415, 0, 0, 0) by the library (the literal of :20-21, not pi).
@@ -47,35 +38,27 @@ ILQR_HD float t_abs(float v) { return ::fabsf(v); }
 struct Acrobot {
   static constexpr int N = 4;
   static constexpr int M = 1;
-  static constexpr int kTrig = 3; /* sincos(q2) (H, C), sin(q1) (G), sin(q1 + q2) (G) */
-
-  template <typename S>
-  ILQR_HD static S trig_arg(int g, const S *x) {
-    return g == 0 ? x[1] : (g == 1 ? x[0] : x[0] + x[1]);
-  }
-  static ILQR_HDC unsigned trig_deps(int g) { return g == 0 ? 2u : (g == 1 ? 1u : 3u); }
-
   /* Acrobot::dynamics :72-81 with H :43-51, C :53-61, G :63-70; parameters :19,23-25
    * (I1 = I2 = l1 = l2 = m1 = m2 = 1, lc = 0.5, g = 9.81).  The 2x2 inverse is the closed form
-   * Eigen uses for fixed-size 2x2 (Eigen/src/LU/InverseImpl.h:76-94).
-   * sn[g], cs[g] = sin, cos of trig_arg(g, x). */
+   * Eigen uses for fixed-size 2x2 (Eigen/src/LU/InverseImpl.h:76-94).  The three sincos
+   * (of q2, q1, q1 + q2; trig.cuh) are independent, which the instruction scheduler exploits. */
   template <typename S>
-  ILQR_HD static void dynamics_trig(const S *x, const S *u, const S * /*mp*/, const S *sn, const S *cs, S *dx) {
+  ILQR_HD static void dynamics(const S *x, const S *u, const S * /*mp*/, S *dx) {
     const S I1 = 1, I2 = 1, l1 = 1, l2 = 1, m1 = 1, m2 = 1, g = S(9.81);
     const S lc1 = S(0.5) * l1, lc2 = S(0.5) * l2;
-    const S qd0 = x[2], qd1 = x[3];
-    const S c2 = cs[0];
+    const S q0 = x[0], q1 = x[1], qd0 = x[2], qd1 = x[3];
+    S c2, s2, s1, s1p2, unused;
+    sincos_det(q1, &s2, &c2);
+    sincos_det(q0, &s1, &unused);
+    sincos_det(q0 + q1, &s1p2, &unused);
     const S H00 = I1 + I2 + m2 * l1 * l1 + 2 * m2 * l1 * lc2 * c2;
     const S H01 = I2 + m2 * l1 * lc2 * c2;
     const S H10 = I2 + m2 * l1 * lc2 * c2;
     const S H11 = I2;
-    const S s2 = sn[0];
     const S C00 = -2 * m2 * l1 * lc2 * s2 * qd1;
     const S C01 = -m2 * l2 * lc2 * s2 * qd1;
     const S C10 = m2 * l1 * lc2 * s2 * qd0;
     const S C11 = 0;
-    const S s1 = sn[1];
-    const S s1p2 = sn[2];
     const S G0 = m1 * g * lc1 * s1 + m2 * g * (l1 * s1 + lc2 * s1p2);
     const S G1 = m2 * g * lc2 * s1p2;
     const S r0 = (S(0) - (C00 * qd0 + C01 * qd1)) - G0; /* Vector2d(0,u) - C*qdot - G */
@@ -87,13 +70,6 @@ struct Acrobot {
     dx[1] = qd1;
     dx[2] = Hi00 * r0 + Hi01 * r1;
     dx[3] = Hi10 * r0 + Hi11 * r1;
-  }
-  template <typename S>
-  ILQR_HD static void dynamics(const S *x, const S *u, const S *mp, S *dx) {
-    S sn[kTrig], cs[kTrig];
-#pragma unroll
-    for (int g = 0; g < kTrig; g++) sincos_det(trig_arg(g, x), &sn[g], &cs[g]);
-    dynamics_trig(x, u, mp, sn, cs, dx);
   }
   /* Acrobot::cost :83-92 — Ks = Kd = 0, Kr = 0.1 */
   template <typename S>
@@ -142,16 +118,6 @@ struct Acrobot {
 struct DoubleIntegrator {
   static constexpr int N = 4;
   static constexpr int M = 2;
-  static constexpr int kTrig = 0;
-
-  template <typename S>
-  ILQR_HD static S trig_arg(int, const S *) { return 0; }
-  static ILQR_HDC unsigned trig_deps(int) { return 0u; }
-  template <typename S>
-  ILQR_HD static void dynamics_trig(const S *x, const S *u, const S *mp, const S *, const S *, S *dx) {
-    dynamics(x, u, mp, dx);
-  }
-
   template <typename S>
   ILQR_HD static void dynamics(const S *x, const S *u, const S * /*mp*/, S *dx) { /* :29-37 */
     const S mass = 1;
@@ -210,14 +176,5 @@ ILQR_HD void integrate(const S *x, const S *u, const S *mp, S dt, S *x1) {
 #pragma unroll
   for (int i = 0; i < Model::N; i++) x1[i] = x[i] + dx[i] * dt;
 }
-/* the same with the sin/cos values supplied (trig protocol above) */
-template <class Model, typename S>
-ILQR_HD void integrate_trig(const S *x, const S *u, const S *mp, S dt, const S *sn, const S *cs, S *x1) {
-  S dx[Model::N];
-  Model::dynamics_trig(x, u, mp, sn, cs, dx);
-#pragma unroll
-  for (int i = 0; i < Model::N; i++) x1[i] = x[i] + dx[i] * dt;
-}
-
 }  // namespace ilqr
 #endif

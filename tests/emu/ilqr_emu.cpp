@@ -38,7 +38,7 @@ struct Emu : EmuBase {
   SolveParams<S> P;
   typename Core<Model, S, CD, HostExec<N, M, S>>::Sc sc;
   HostExec<N, M, S> ex;
-  std::vector<S> x0, xs, us, K, k, Vx0, Vxx0, gterm;
+  std::vector<S> x0, xs, us, K, k, Vx0, Vxx0, gterm, bufF, bufC, candX, candU;
   TrajState<S> st;
   int T = 0;
 
@@ -60,7 +60,16 @@ struct Emu : EmuBase {
     t.st = &st;
     return t;
   }
-  Core<Model, S, CD, HostExec<N, M, S>> core() { return Core<Model, S, CD, HostExec<N, M, S>>(P, sc, gterm.data(), ex, ptrs()); }
+  SlotPtrs<S> slot() {
+    SlotPtrs<S> w;
+    w.F = bufF.data();
+    w.C = bufC.data();
+    w.cand_x = candX.data();
+    w.cand_u = candU.data();
+    w.gterm = gterm.data();
+    return w;
+  }
+  Core<Model, S, CD, HostExec<N, M, S>> core() { return Core<Model, S, CD, HostExec<N, M, S>>(P, sc, ex, ptrs(), slot()); }
 
   double init(const double *x0_, const double *u0_, int T_) override {
     T = T_;
@@ -74,6 +83,10 @@ struct Emu : EmuBase {
     Vx0.assign(N, 0);
     Vxx0.assign(N * N, 0);
     gterm.assign(T, 0);
+    bufF.assign((size_t)T * (N + M) * N, 0);
+    bufC.assign((size_t)T * Scratch<N, M, S, CD>::NC, 0);
+    candX.assign((size_t)P.n_alpha * T * N, 0);
+    candU.assign((size_t)P.n_alpha * T * M, 0);
     for (int i = 0; i < N; i++) x0[i] = S(x0_[i]);
     for (int i = 0; i < T * M; i++) us[i] = S(u0_[i]);
     core().op_init();
