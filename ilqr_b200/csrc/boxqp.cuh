@@ -279,15 +279,20 @@ ILQR_HD void box_qp_generic(const QPParams<S> &p, QPWork<M, S> &w) {
   if (w.result >= 1 && any_free) rinv_rtinv(w, w.r_dim, w.Hinv);
 }
 
-/* m == 1: the same arithmetic on scalars held in registers */
+/* m == 1: the same arithmetic on scalars held in registers.  Three values the general code
+ * recomputes are reused here because they are bit-identical by construction: 1/R is formed once
+ * for R^-1 and R^-T (the same division), sqrt(grad^2) is |grad| (exact in IEEE-754 away from
+ * over/underflow, where both sides of the `< minGrad` test agree anyway), and the R^-1 R^-T the
+ * gain computation needs (ilqr_core.cpp:379) is the one of the last Newton step because R is only
+ * ever factorised once when there is a single variable. */
 template <typename S>
 ILQR_HD void box_qp_scalar(const QPParams<S> &p, QPWork<1, S> &w) {
   const S Q = w.Q[0], c = w.c[0], lo = w.lo[0], hi = w.hi[0];
   S x = clampd(w.x0[0], lo, hi);
   S val = (x * Q) * x + x * c;
   S oldvalue = 0;
-  S clamped = 0, old_clamped;
-  S R = 0;
+  S R = 0, Hinv = 0;
+  bool have_hinv = false;
   int result = 0, vfree = 1;
   for (int iter = 0; iter <= p.max_iter; iter++) {
     if (iter > 0 && (oldvalue - val) < p.min_rel_improve * t_abs(oldvalue)) {
@@ -296,26 +301,24 @@ ILQR_HD void box_qp_scalar(const QPParams<S> &p, QPWork<1, S> &w) {
     }
     const S grad = Q * x + c;
     oldvalue = val;
-    old_clamped = clamped;
-    clamped = 0;
     vfree = 1;
     if ((t_abs(x - lo) < p.clamp_tol && grad > 0) || (t_abs(x - hi) < p.clamp_tol && grad < 0)) {
-      clamped = 1;
       vfree = 0;
-    }
-    if (clamped != 0) {
       result = 6;
       break;
     }
-    if (iter == 0 || (old_clamped - clamped) != 0) R = (Q <= 0) ? Q : t_sqrt(Q);
-    const S gn = t_sqrt(grad * grad);
-    if (gn < p.min_grad) {
+    /* the flag difference of :80 is 0 - 0 here (a clamped variable has just left the loop): factorise at iter 0 only */
+    if (iter == 0) R = (Q <= 0) ? Q : t_sqrt(Q);
+    if (t_abs(grad) < p.min_grad) { /* sqrt(grad * grad) */
       result = 5;
       break;
     }
-    const S grad_clamped = Q * (x * clamped) + c;
-    const S Ri = S(1) / R, Rti = S(1) / R;
-    const S Hinv = Ri * Rti;
+    const S grad_clamped = Q * (x * S(0)) + c;
+    if (!have_hinv) {
+      const S Ri = S(1) / R;
+      Hinv = Ri * Ri;
+      have_hinv = true;
+    }
     const S search = (-Hinv) * grad_clamped - x;
     /* quadclamp_line_search */
     const S slope = search * grad;
@@ -350,8 +353,11 @@ ILQR_HD void box_qp_scalar(const QPParams<S> &p, QPWork<1, S> &w) {
   w.r_dim = 1;
   w.result = result;
   if (result >= 1 && vfree) {
-    const S Ri = S(1) / R, Rti = S(1) / R;
-    w.Hinv[0] = Ri * Rti;
+    if (!have_hinv) {
+      const S Ri = S(1) / R;
+      Hinv = Ri * Ri;
+    }
+    w.Hinv[0] = Hinv;
   }
 }
 

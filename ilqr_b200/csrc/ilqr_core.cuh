@@ -497,10 +497,9 @@ struct Core {
         }
       }
     });
-    /* symmetrise (:393), roll the value function, remember k for the next warm start, stage k / K
-     * (:396-397) and the gradient-norm term of this timestep (:405-412) */
+    /* symmetrise (:393), roll the value function, remember k for the next warm start, stage k / K (:396-397) */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + N + M + M * N + M + 1; e += 32) {
+      for (int e = lane; e < N * N + N + M + M * N + M; e += 32) {
         if (e < N * N) {
           const int a = e / N, b = e % N;
           sc.Vxx[e] = S(0.5) * (sc.Vtmp[a * N + b] + sc.Vtmp[b * N + a]);
@@ -510,10 +509,8 @@ struct Core {
           sc.kprev[e - N * N - N] = sc.kc[e - N * N - N];
         } else if (e < N * N + N + M + M * N) {
           sc.K[tt * M * N + e - (N * N + N + M)] = sc.Kc[e - (N * N + N + M)];
-        } else if (e < N * N + N + M + M * N + M) {
-          sc.k[tt * M + e - (N * N + N + M + M * N)] = sc.kc[e - (N * N + N + M + M * N)];
         } else {
-          sl.gterm[tt] = gn_term(sc.kc, ut); /* caller offsets sl.gterm to the tile */
+          sc.k[tt * M + e - (N * N + N + M + M * N)] = sc.kc[e - (N * N + N + M + M * N)];
         }
       }
     });
@@ -523,7 +520,6 @@ struct Core {
   /* iLQR::backward_pass.  Returns the failing timestep or 0 (:371,400). */
   ILQR_HD int backward_pass(S lam) {
     const int T = P.T;
-    S *const gterm_base = sl.gterm;
     ex.lanes([&](int lane, Lane &) {
       if (lane < N) sc.x[lane] = tr.xs[T * N + lane];
       if (lane < M) {
@@ -549,7 +545,6 @@ struct Core {
           for (int e = lane; e < cnt * NC; e += 32) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NC + e);
         }
       });
-      sl.gterm = gterm_base + t0;
       int first_done = 0; /* tile entries [first_done, cnt) hold finished k / K */
       for (int tt = cnt - 1; tt >= 0; tt--) {
         if (!backward_step(tt, lam)) { /* the steps above this one have already written their k, K (:396-397) */
@@ -558,12 +553,13 @@ struct Core {
           break;
         }
       }
+      /* flush the tile's k / K and the gradient-norm terms of its timesteps (:405-412), one per lane */
       ex.lanes([&](int lane, Lane &) {
         for (int e = lane + first_done * M * N; e < cnt * M * N; e += 32) tr.K[t0 * M * N + e] = sc.K[e];
         for (int e = lane + first_done * M; e < cnt * M; e += 32) tr.k[t0 * M + e] = sc.k[e];
+        for (int e = lane + first_done; e < cnt; e += 32) sl.gterm[t0 + e] = gn_term(sc.k + e * M, sc.us + e * M);
       });
     }
-    sl.gterm = gterm_base;
     if (diverged_at >= 0) return diverged_at;
     /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
     ex.lanes([&](int lane, Lane &) {
