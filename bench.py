@@ -248,7 +248,8 @@ def ours_arm(args, cfg):
     n, m = 4, 1
     cd = abi.COST_ANALYTIC if cfg["cost_deriv"] == "analytic" else abi.COST_FD
     kw = dict(u_min=[-cfg["limits"]], u_max=[cfg["limits"]]) if cfg["limits"] else {}
-    x0, u0 = synth_inputs(B, T, SEED + rank)  # every rank owns different instances
+    from ilqr_b200 import shard
+    x0, u0 = synth_inputs(B, T, shard.rank_seed(SEED, rank))  # every rank owns different instances
     solver = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cd, device=local, **kw)
     stream = torch.cuda.ExternalStream(solver.stream, device=dev)
 
@@ -258,7 +259,6 @@ def ours_arm(args, cfg):
     iters_h = torch.empty(B, dtype=torch.int32).pin_memory()
     x0_d, u0_d = x0_h.to(dev), u0_h.to(dev)
     cost_d = torch.empty(B, dtype=torch.float64, device=dev)
-    gathered = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
 
@@ -266,8 +266,7 @@ def ours_arm(args, cfg):
         return torch.cuda.Event(enable_timing=True)
 
     def gather_costs():
-        if world > 1:
-            dist.gather(cost_d, gathered, dst=0)
+        return shard.gather_final_costs(cost_d, dst=0)  # the one collective of the job (NCCL over NVLink when N > 1)
 
     def step_resident():
         """inputs resident in HBM -> final costs resident in HBM (rank 0 after the gather)"""
@@ -346,12 +345,7 @@ def ours_arm(args, cfg):
     clocks = sampler.stop() if rank == 0 else None
 
     # whole-job numbers: sum of trips over ranks / max time over ranks
-    t_res = torch.tensor([sum(step_ms), sum(e2e_ms), sum(solve_ms)], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([trips, trips_e2e, acc, rej], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_res, cnt = t_res.tolist(), cnt.tolist()
+    t_res, cnt = shard.reduce_step_stats([sum(step_ms), sum(e2e_ms), sum(solve_ms)], [trips, trips_e2e, acc, rej], dev)
     if rank == 0:
         value = cnt[0] / (t_res[0] * 1e-3)
         e2e = cnt[1] / (t_res[1] * 1e-3)

@@ -1,0 +1,85 @@
+/*
+ * ilqr.h — drop-in replacement for the reference's include/ilqr.h: the same `class iLQR`
+ * (constructor taking ownership of a `Model*`, the three `generate_trajectory` overloads,
+ * `init_traj`, `output_to_csv`; reference include/ilqr.h:28-54), implemented on libilqr_b200.so
+ * through the C ABI (include/ilqr_b200.h) instead of the Eigen loops of src/ilqr_core.cpp.
+ *
+ * Put this directory BEFORE the reference's include/ on the include path: the reference's own
+ * model.h, common.h, acrobot.h, double_integrator.h and its src/run_ilqr.cpp then compile
+ * unchanged against it (ilqr_b200/host/Makefile does exactly that).  On top of the reference's
+ * surface it adds what the reference keeps private (read access to xs, us, K, k, cost) and a
+ * batched entry point, since one trajectory cannot fill a B200.
+ *
+ * A Model subclass runs on the GPU through a hand-written device twin (ilqr_b200/csrc/models.cuh).
+ * The constructor recognises the reference's Acrobot and DoubleIntegrator by RTTI, checks the twin
+ * against the host object's own dynamics / cost / final_cost on random probes, and throws
+ * std::runtime_error for any other subclass or on a mismatch: there is no CPU fallback.
+ */
+#ifndef _ILQR_H_
+#define _ILQR_H_
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "model.h"
+
+struct ilqr_handle;
+
+class iLQR {
+ public:
+  iLQR(Model *p_dyn, double timeDelta);
+  ~iLQR();
+  iLQR(const iLQR &) = delete;
+  iLQR &operator=(const iLQR &) = delete;
+
+  /* the reference's public methods (include/ilqr.h:49-54) */
+  void generate_trajectory();                                          /* continue the current solve      */
+  void generate_trajectory(const VectorXd &x_0);                       /* warm start, src/ilqr_core.cpp:65-76 */
+  void generate_trajectory(const VectorXd &x_0, const VecOfVecXd &u0); /* fresh solve, :59-62             */
+  void output_to_csv(const std::string filename);                      /* :414-431                        */
+  double init_traj(const VectorXd &x_0, const VecOfVecXd &u_0);        /* :11-56, returns the initial cost */
+
+  /* what the reference keeps private (include/ilqr.h:57-85) */
+  const VecOfVecXd &get_xs() const { return xs; }
+  const VecOfVecXd &get_us() const { return us; }
+  const VecOfVecXd &get_k() const { return k; }
+  const VecOfMatXd &get_K() const { return K; }
+  double get_cost() const { return cost_s; }
+  int get_iterations() const { return iterations; }
+  int get_status() const { return status; } /* ILQR_EXIT_* of include/ilqr_b200.h */
+
+  /* B independent problems at once: X0 is B x n, U0[b] the T initial controls of problem b.
+   * Returns the final costs; the trajectory of problem b is then available through batch_xs(b) etc. */
+  std::vector<double> solve_batch(const std::vector<VectorXd> &X0, const std::vector<VecOfVecXd> &U0);
+  VecOfVecXd batch_xs(int b) const;
+  VecOfVecXd batch_us(int b) const;
+  int batch_iterations(int b) const { return batch_iters.at(b); }
+
+  std::shared_ptr<Model> model;
+  double dt;
+  int T = 0;
+  /* solver settings the reference hard-codes at file scope (include/ilqr.h:14-22); defaults are the reference's */
+  int maxIter = 100;
+  bool quiet = false; /* the reference prints a progress table; here only the banner lines survive */
+  int cost_deriv = 0; /* ILQR_COST_FD (the reference's behaviour) | ILQR_COST_ANALYTIC */
+
+ private:
+  void create(long B, int T_);
+  void fetch_single();
+  ilqr_handle *h = nullptr;
+  long hB = 0;
+  int hT = 0;
+  int model_id = -1;
+  double model_params[16] = {0};
+  VecOfVecXd xs, us, k;
+  VecOfMatXd K;
+  double cost_s = 0;
+  int iterations = 0, status = 0;
+  std::vector<double> bxs, bus;
+  std::vector<int> batch_iters;
+};
+
+#endif

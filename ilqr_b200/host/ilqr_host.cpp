@@ -1,0 +1,220 @@
+// ilqr_host.cpp — `class iLQR` of ilqr_b200/host/ilqr.h on top of the C ABI (include/ilqr_b200.h).
+// Host orchestration only: marshal Eigen containers to the ABI's row-major arrays, call the library,
+// marshal back.  No solver arithmetic happens here.
+#include <stdio.h>
+#include <string.h>
+
+#include <random>
+#include <typeinfo>
+
+// The reference's model headers keep their parameters private (acrobot.h:112-118,
+// double_integrator.h:50-53).  The device twin of DoubleIntegrator needs the goal the object was
+// built with; reading it here keeps those headers unchanged.
+#include "common.h"  // everything the model headers pull in (std, Eigen) is included before the next line
+#include "model.h"
+#define private public
+#include "acrobot.h"
+#include "double_integrator.h"
+#undef private
+
+#include "../../include/ilqr_b200.h"
+#include "../csrc/models.cuh"  // host instantiation of the device twins, for the construction-time check
+#include "ilqr.h"
+
+namespace {
+
+void check(int rc, ilqr_handle *h, const char *what) {
+  if (rc != ILQR_OK) throw std::runtime_error(std::string(what) + ": " + ilqr_last_error(h));
+}
+
+template <class Twin>
+void verify_twin(Model &m, const double *mp, double dt) {
+  std::mt19937_64 g(7);
+  std::uniform_real_distribution<double> U(-3.0, 3.0);
+  for (int probe = 0; probe < 16; probe++) {
+    VectorXd x(Twin::N), u(Twin::M);
+    double xa[Twin::N], ua[Twin::M], x1[Twin::N];
+    for (int i = 0; i < Twin::N; i++) x(i) = xa[i] = U(g);
+    for (int i = 0; i < Twin::M; i++) u(i) = ua[i] = U(g);
+    const VectorXd ref = m.integrate_dynamics(x, u, dt);
+    ilqr::integrate<Twin, double>(xa, ua, mp, dt, x1);
+    double err = 0;
+    for (int i = 0; i < Twin::N; i++) err = std::max(err, std::fabs(ref(i) - x1[i]));
+    err = std::max(err, std::fabs(m.cost(x, u) - Twin::cost(xa, ua, mp)) / (1 + std::fabs(m.cost(x, u))));
+    err = std::max(err, std::fabs(m.final_cost(x) - Twin::final_cost(xa, mp)) / (1 + std::fabs(m.final_cost(x))));
+    if (!(err < 1e-11))
+      throw std::runtime_error("iLQR: the device twin of this Model disagrees with the host object (edited model header?)");
+  }
+}
+
+}  // namespace
+
+iLQR::iLQR(Model *p_dyn, double timeDelta) : dt(timeDelta) {
+  model.reset(p_dyn);  // takes ownership, like the reference (include/ilqr.h:30-31)
+  if (Acrobot *a = dynamic_cast<Acrobot *>(p_dyn)) {
+    model_id = ILQR_MODEL_ACROBOT;
+    for (int i = 0; i < 4; i++) model_params[i] = a->goal(i);
+    verify_twin<ilqr::Acrobot>(*p_dyn, model_params, dt);
+  } else if (DoubleIntegrator *d = dynamic_cast<DoubleIntegrator *>(p_dyn)) {
+    model_id = ILQR_MODEL_DOUBLE_INTEGRATOR;
+    for (int i = 0; i < 4; i++) model_params[i] = d->goal(i);
+    verify_twin<ilqr::DoubleIntegrator>(*p_dyn, model_params, dt);
+  } else {
+    throw std::runtime_error(std::string("iLQR: no device twin for Model subclass ") + typeid(*p_dyn).name() +
+                             " (ilqr_b200/csrc/models.cuh); there is no CPU fallback");
+  }
+}
+
+iLQR::~iLQR() { ilqr_destroy(h); }
+
+void iLQR::create(long B, int T_) {
+  if (h && hB == B && hT == T_) return;
+  ilqr_destroy(h);
+  h = nullptr;
+  ilqr_desc d;
+  memset(&d, 0, sizeof(d));
+  d.model_id = model_id;
+  d.dtype = ILQR_F64;
+  d.cost_deriv = cost_deriv;
+  d.device = 0;
+  d.T = T_;
+  d.B = B;
+  d.dt = dt;
+  d.override_limits = 1;  // Model::u_min / u_max are public data the caller may have changed (model.h:17)
+  for (int j = 0; j < model->u_dims; j++) {
+    d.u_min[j] = model->u_min(j);
+    d.u_max[j] = model->u_max(j);
+  }
+  for (int i = 0; i < 16; i++) d.model_params[i] = model_params[i];
+  ilqr_default_params(&d.params);
+  d.params.max_iter = maxIter;
+  check(ilqr_create(&d, &h), nullptr, "ilqr_create");
+  hB = B;
+  hT = T_;
+}
+
+double iLQR::init_traj(const VectorXd &x_0, const VecOfVecXd &u_0) {
+  T = (int)u_0.size();
+  const int n = model->x_dims, m = model->u_dims;
+  create(1, T);
+  std::vector<double> x0(n), u0((size_t)T * m);
+  for (int i = 0; i < n; i++) x0[i] = x_0(i);
+  for (int t = 0; t < T; t++)
+    for (int j = 0; j < m; j++) u0[(size_t)t * m + j] = u_0[t](j);
+  check(ilqr_set_initial(h, x0.data(), u0.data(), 0), h, "ilqr_set_initial");
+  fetch_single();
+  if (!quiet) printf("Initial cost: %f\n", cost_s);
+  return cost_s;
+}
+
+void iLQR::fetch_single() {
+  const int n = model->x_dims, m = model->u_dims;
+  std::vector<double> bx((size_t)(T + 1) * n), bu((size_t)T * m), bk((size_t)T * m), bK((size_t)T * m * n);
+  check(ilqr_get(h, ILQR_F_XS, bx.data(), 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_US, bu.data(), 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_KFF, bk.data(), 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_K, bK.data(), 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_COST, &cost_s, 0), h, "ilqr_get");
+  int32_t it = 0, st = 0;
+  check(ilqr_get(h, ILQR_F_ITERS, &it, 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_STATUS, &st, 0), h, "ilqr_get");
+  iterations = it;
+  status = st;
+  xs.assign(T + 1, VectorXd::Zero(n));
+  us.assign(T, VectorXd::Zero(m));
+  k.assign(T, VectorXd::Zero(m));
+  K.assign(T, MatrixXd::Zero(m, n));
+  for (int t = 0; t <= T; t++)
+    for (int i = 0; i < n; i++) xs[t](i) = bx[(size_t)t * n + i];
+  for (int t = 0; t < T; t++) {
+    for (int j = 0; j < m; j++) {
+      us[t](j) = bu[(size_t)t * m + j];
+      k[t](j) = bk[(size_t)t * m + j];
+      for (int i = 0; i < n; i++) K[t](j, i) = bK[((size_t)t * m + j) * n + i];
+    }
+  }
+}
+
+void iLQR::generate_trajectory(const VectorXd &x_0, const VecOfVecXd &u0) {
+  init_traj(x_0, u0);
+  generate_trajectory();
+}
+
+void iLQR::generate_trajectory(const VectorXd &x_0) {
+  if (!h) throw std::runtime_error("iLQR::generate_trajectory(x_0): no previous solve to warm-start from");
+  std::vector<double> x0(model->x_dims);
+  for (int i = 0; i < model->x_dims; i++) x0[i] = x_0(i);
+  check(ilqr_warm_start(h, x0.data(), 0), h, "ilqr_warm_start");
+  generate_trajectory();
+}
+
+void iLQR::generate_trajectory() {
+  if (!h) throw std::runtime_error("iLQR::generate_trajectory(): call init_traj first");
+  check(ilqr_solve(h), h, "ilqr_solve");
+  fetch_single();
+  if (!quiet) {
+    static const char *why[] = {"running", "gradient norm < tolGrad", "cost change < tolFun", "lambda > lambdaMax", "max iterations"};
+    printf("\nEXIT: %s after %d iterations, cost %.12g\n", why[status], iterations, cost_s);
+  }
+  output_to_csv("ilqr_result.csv");  // the reference does this at the end of every solve (src/ilqr_core.cpp:300)
+}
+
+// src/ilqr_core.cpp:414-431: header "x1, ..., xn, u0, ..., um" (the reference names one control column too many,
+// :418-419, kept), one %f row per knot, the last row states only.
+void iLQR::output_to_csv(const std::string filename) {
+  FILE *f = fopen(filename.c_str(), "w");
+  if (!f) return;
+  const int n = model->x_dims, m = model->u_dims;
+  for (int i = 0; i < n; i++) fprintf(f, "x%d, ", i + 1);
+  for (int j = 0; j <= m; j++) fprintf(f, j < m ? "u%d, " : "u%d", j);
+  fprintf(f, "\n");
+  for (int t = 0; t <= T; t++) {
+    for (int i = 0; i < n; i++) fprintf(f, "%f, ", xs[t](i));
+    if (t < T)
+      for (int j = 0; j < m; j++) fprintf(f, "%f, ", us[t](j));
+    fprintf(f, "\n");
+  }
+  fclose(f);
+}
+
+std::vector<double> iLQR::solve_batch(const std::vector<VectorXd> &X0, const std::vector<VecOfVecXd> &U0) {
+  const long B = (long)X0.size();
+  if (B == 0 || U0.size() != X0.size()) throw std::runtime_error("iLQR::solve_batch: X0 and U0 must have the same non-zero length");
+  const int n = model->x_dims, m = model->u_dims;
+  T = (int)U0[0].size();
+  create(B, T);
+  std::vector<double> x0((size_t)B * n), u0((size_t)B * T * m);
+  for (long b = 0; b < B; b++) {
+    if ((int)U0[b].size() != T) throw std::runtime_error("iLQR::solve_batch: ragged horizons");
+    for (int i = 0; i < n; i++) x0[(size_t)b * n + i] = X0[b](i);
+    for (int t = 0; t < T; t++)
+      for (int j = 0; j < m; j++) u0[((size_t)b * T + t) * m + j] = U0[b][t](j);
+  }
+  check(ilqr_set_initial(h, x0.data(), u0.data(), 0), h, "ilqr_set_initial");
+  check(ilqr_solve(h), h, "ilqr_solve");
+  std::vector<double> cost(B);
+  std::vector<int32_t> iters(B);
+  bxs.resize((size_t)B * (T + 1) * n);
+  bus.resize((size_t)B * T * m);
+  check(ilqr_get(h, ILQR_F_COST, cost.data(), 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_ITERS, iters.data(), 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_XS, bxs.data(), 0), h, "ilqr_get");
+  check(ilqr_get(h, ILQR_F_US, bus.data(), 0), h, "ilqr_get");
+  batch_iters.assign(iters.begin(), iters.end());
+  return cost;
+}
+
+VecOfVecXd iLQR::batch_xs(int b) const {
+  const int n = model->x_dims;
+  VecOfVecXd out(T + 1, VectorXd::Zero(n));
+  for (int t = 0; t <= T; t++)
+    for (int i = 0; i < n; i++) out[t](i) = bxs[((size_t)b * (T + 1) + t) * n + i];
+  return out;
+}
+VecOfVecXd iLQR::batch_us(int b) const {
+  const int m = model->u_dims;
+  VecOfVecXd out(T, VectorXd::Zero(m));
+  for (int t = 0; t < T; t++)
+    for (int j = 0; j < m; j++) out[t](j) = bus[((size_t)b * T + t) * m + j];
+  return out;
+}

@@ -15,6 +15,9 @@ f64 kernels reproduce the oracle's arithmetic order without FMA, so
     termination the bulk must agree to 1e-6 and a small fraction of bifurcated instances is
     tolerated (SURVEY.md §7 "Parity methodology").
 """
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -372,3 +375,49 @@ def test_f32_config3_sanity():
     s.iterate(10)
     c1 = s.get("cost")
     assert np.isfinite(c1).all() and (c1 <= c0).all() and c1.mean() < 0.8 * c0.mean()
+
+
+# ---------------------------------------------------------------------------------------------
+# the C++ host layer: the reference's UNCHANGED src/run_ilqr.cpp, acrobot.h, double_integrator.h
+# compiled against ilqr_b200/host/ilqr.h (prebuilt in the dev container, ilqr_b200/host/Makefile)
+# ---------------------------------------------------------------------------------------------
+HOST_BUILD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ilqr_b200", "host", "_build")
+
+
+def _read_csv(path):
+    rows = open(path).read().strip().split("\n")[1:]
+    return [np.array([float(v) for v in r.strip().rstrip(",").split(",")]) for r in rows]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(HOST_BUILD, "run_iLQR")), reason="host binaries not built")
+@pytest.mark.parametrize("which,case", [("acrobot", "acrobot_cli_T499"), ("integrator", "integrator_cli_T99")])
+def test_reference_cli_runs_on_the_gpu_path(tmp_path, golden_solver, which, case):
+    """BASELINE configs[0]: `./run_iLQR acrobot` — the reference's own main(), on libilqr_b200.so."""
+    out = subprocess.run([os.path.join(HOST_BUILD, "run_iLQR"), which], cwd=tmp_path, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "Run iLQR!" in out.stdout and "iLQR took:" in out.stdout          # src/run_ilqr.cpp:57,62
+    rows = _read_csv(tmp_path / "ilqr_result.csv")                            # src/ilqr_core.cpp:300,414-431
+    g = golden_solver
+    xs = g[case + "/final_xs"]
+    assert len(rows) == xs.shape[0]
+    assert np.allclose(rows[-1][:4], xs[-1], atol=2e-6)                       # %f keeps 6 decimals
+    assert np.allclose(np.stack([r[:4] for r in rows]), xs, atol=5e-5)
+    cost = float(out.stdout.split("cost ")[-1].split()[0])
+    assert abs(cost - g[case + "/final_cost"]) <= 1e-6 * abs(cost)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(HOST_BUILD, "batch_demo")), reason="host binaries not built")
+def test_host_batch_entry_point(tmp_path, golden_solver):
+    out = subprocess.run([os.path.join(HOST_BUILD, "batch_demo"), "32", "200"], cwd=tmp_path, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.strip().split("\n")]
+    g = golden_solver
+    ok = 0
+    for b in range(6):
+        cost = float(lines[b][3])
+        ok += abs(cost - g["acrobot_T200_b%d/final_cost" % b]) <= 1e-6 * abs(cost)
+    assert ok >= 4                                                            # FD-cost mode, bifurcations tolerated
+    single = lines[6]
+    assert abs(float(single[3]) - float(lines[0][3])) <= 1e-9 * abs(float(lines[0][3]))  # single API == batch entry 0

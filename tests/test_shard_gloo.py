@@ -1,0 +1,71 @@
+"""CPU, world_size 2 over gloo: the N > 1 host logic of bench.py (ilqr_b200/shard.py) — block ownership,
+the single gather of final costs in rank order, and max-time / sum-count reduction."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ilqr_b200 import shard
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B = 6
+        # every rank "solves" its own block: cost of instance b is a function of its GLOBAL index
+        lo, hi = shard.shard_bounds(B * world, world, rank)
+        local = torch.arange(lo, hi, dtype=torch.float64) * 1.5 + 0.25
+        got = shard.gather_final_costs(local, dst=0)
+        t, c = shard.reduce_step_stats([10.0 + rank, 3.0 - rank], [100 + rank, 7], torch.device("cpu"))
+        if rank == 0:
+            out.put(("costs", got.numpy().tolist()))
+            out.put(("stats", t, c))
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_the_batch():
+    for total, world in ((4096, 1), (1048576, 8), (10, 3), (7, 8)):
+        blocks = [shard.shard_bounds(total, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == total
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard.shard_bounds(1048576, 8, 3) == (393216, 524288)   # BASELINE configs[4]: 131 072 per GPU
+    assert shard.rank_seed(12345, 0) == 12345 and shard.rank_seed(12345, 5) == 12350
+
+
+def test_gather_of_final_costs_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    msgs = [out.get(timeout=10) for _ in range(2)]
+    costs = next(m for m in msgs if m[0] == "costs")[1]
+    stats = next(m for m in msgs if m[0] == "stats")
+    assert np.allclose(costs, np.arange(12) * 1.5 + 0.25)          # rank order == global instance order
+    assert stats[1] == [11.0, 3.0] and stats[2] == [201.0, 14.0]    # MAX of times, SUM of counts
+
+
+def test_single_process_is_identity():
+    x = torch.arange(4, dtype=torch.float64)
+    assert shard.gather_final_costs(x) is x
