@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) ilqr_warp_kernel(co
   const size_t slot = (size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   SlotPtrs<S> sl;
   sl.F = a.slotF + slot * (size_t)T * (N + M) * N;
-  sl.C = a.slotC ? a.slotC + slot * (size_t)T * Sc::NC : nullptr;
+  sl.C = a.slotC ? a.slotC + slot * (size_t)T * Sc::NCF : nullptr;
   sl.cand_x = a.slotCandX + slot * (size_t)a.P.n_alpha * T * N;
   sl.cand_u = a.slotCandU + slot * (size_t)a.P.n_alpha * T * M;
   sl.gterm = reinterpret_cast<S *>(mine + sizeof(Sc));
@@ -210,7 +210,7 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
     CU(h, cudaStreamSynchronize(h->stream));
     void **bufs[] = {&h->slotF, &h->slotC, &h->slotCandX, &h->slotCandU};
     const size_t T = (size_t)h->desc.T, na = (size_t)h->desc.params.n_alpha;
-    const size_t per[] = {T * (N + M) * N, CD == kCostFD ? T * Scratch<N, M, S, CD>::NC : 0, na * T * N, na * T * M};
+    const size_t per[] = {T * (N + M) * N, CD == kCostFD ? T * Scratch<N, M, S, CD>::NCF : 0, na * T * N, na * T * M};
     for (int i = 0; i < 4; i++) {
       if (*bufs[i]) CU(h, cudaFree(*bufs[i]));
       *bufs[i] = nullptr;

@@ -91,7 +91,7 @@ struct TrajPtrs {
 template <typename S>
 struct SlotPtrs {
   S *F;      /* [T][n+m][n]   Jacobian columns of the Euler step: F[t][j][r] = d x'_r / d (x|u)_j   */
-  S *C;      /* [T][NC]       finite-difference cost derivatives (cx cu cxx cxu cuu), FD mode only  */
+  S *C;      /* [T][NCF]      finite-difference cost derivatives, full layout, FD mode only          */
   S *cand_x; /* [n_alpha][T][n]  candidate states x_1..x_T of the line search                       */
   S *cand_u; /* [n_alpha][T][m]  candidate controls                                                  */
   S *gterm;  /* [T] per-timestep terms of the gradient norm (shared memory on the device)           */
@@ -101,19 +101,23 @@ struct SlotPtrs {
 template <int N, int M, typename S, int CD>
 struct Scratch {
   static constexpr int NM = N + M;
-  static constexpr int NC = N + M + N * N + N * M + M * M;
+  static constexpr int NA = N + 1;              /* columns of an x-indexed matrix augmented with its vector */
+  static constexpr int NCF = NM + NM * NM;      /* cost derivatives of one timestep, full layout (Core::cost_stencil) */
   /* staged tiles: rollouts use kTile timesteps, the backward pass the first kTileB of the same arrays */
   S xs[kTile * N], us[kTile * M], K[kTile * M * N], k[kTile * M];
-  S Ft[kTileB * NM * N];                     /* backward: Jacobian columns of the tile      */
-  S Ct[CD == kCostFD ? kTileB * NC : 1];     /* backward: FD cost derivatives of the tile   */
+  S Ft[kTileB * NM * N];                     /* backward: Jacobian columns of the tile                 */
+  S Ct[CD == kCostFD ? kTileB * NCF : 1];    /* backward: FD cost derivatives of the tile (full layout) */
   /* one timestep */
-  S x[N], u[M];
-  S cx[N], cu[M], cxx[N * N], cxu[N * M], cuu[M * M]; /* terminal / analytic cost derivatives */
-  S Vx[N], Vxx[N * N];  /* value function at i+1, overwritten with i at the end of the step */
-  S W[NM * N];          /* F^T Vxx' */
-  S Qx[N], Qu[M], Qxx[N * N], Qux[M * N], Quu[M * M];
-  S Kc[M * N], kc[M], kprev[M];
-  S Vtmp[N * N], Vxn[N];
+  S x[N], u[M];         /* xs[T] and a zero control for the terminal derivatives */
+  S Cf[NCF];            /* terminal / closed-form cost derivatives, full layout */
+  S Va[N * NA];         /* [Vxx | Vx] at i+1, overwritten with i at the end of the step */
+  S W[NM * NA];         /* F^T [Vxx' | Vx'] */
+  S Qxa[N * NA];        /* [Qxx | Qx] */
+  S Qua[M * NA];        /* [Qux | Qu] */
+  S Quu[M * M];
+  S Ka[M * NA];         /* [K_i | k_i] */
+  S kprev[M];
+  S Vt[N * NA];         /* [Vxx | Vx] before symmetrisation */
   S newcost[kMaxAlpha];
   QPWork<M, S> qp;
   TrajState<S> st;
@@ -150,6 +154,19 @@ struct HostExec {
   }
 };
 
+/* Accumulates products in index order.  The reference's sums start from zero (Eigen zero-initialises, the
+ * oracle writes `acc = 0; acc += ...`); 0 + p == p for every p except the sign of a zero, so the first
+ * product is taken as it is and one dependent add per dot product is saved. */
+template <typename S>
+struct Acc {
+  S v = 0;
+  bool any = false;
+  ILQR_HD void add(S p) {
+    v = any ? v + p : p;
+    any = true;
+  }
+};
+
 /* read that must see what another lane of this warp stored to global memory before the last barrier */
 template <typename S>
 ILQR_HD S ld_fresh(const S *p) {
@@ -165,7 +182,7 @@ struct Core {
   static constexpr int N = Model::N, M = Model::M, NM = N + M;
   using Sc = Scratch<N, M, S, CD>;
   using Lane = LaneRegs<N, M, S>;
-  static constexpr int NC = Sc::NC;
+  static constexpr int NA = Sc::NA, NCF = Sc::NCF;
 
   const SolveParams<S> &P;
   Sc &sc;
@@ -208,7 +225,17 @@ struct Core {
     j = i + o;
   }
 
-  ILQR_HD void cost_stencil(int o, bool terminal, const S *x, const S *u, S *cx, S *cu, S *cxx, S *cxu, S *cuu) {
+  /* Cost derivatives of one timestep are kept in ONE array ("full layout", NCF scalars):
+   *   cvec[c]     at [c]                 c < n: cx,  c >= n: cu
+   *   Cfull[c][d] at [NM + c*NM + d]     the (n+m)^2 Hessian [[cxx, cxu], [cxu^T, cuu]]
+   * so that every Q-function entry is the same expression  Cfull[c][d] + sum_r W[c][r] F[d][r]
+   * and the warp phase that evaluates them has a single code path. */
+  ILQR_HD static int ix_cxx(int i, int j) { return NM + i * NM + j; }
+  ILQR_HD static int ix_cxu(int i, int j) { return NM + i * NM + N + j; }
+  ILQR_HD static int ix_cux(int j, int i) { return NM + (N + j) * NM + i; }
+  ILQR_HD static int ix_cuu(int i, int j) { return NM + (N + i) * NM + N + j; }
+
+  ILQR_HD void cost_stencil(int o, bool terminal, const S *x, const S *u, S *cf) {
     const S eps = P.fd_eps;
     const S *mp = P.mp;
     S xa[N], ua[M];
@@ -218,7 +245,7 @@ struct Core {
       const S p = fx(xa, u);
       perturb<N>(x, o, -eps, -1, S(0), xa);
       const S m = fx(xa, u);
-      cx[o] = (p - m) / (2 * eps);
+      cf[o] = (p - m) / (2 * eps);
       return;
     }
     o -= N;
@@ -228,7 +255,7 @@ struct Core {
         const S p = Model::cost(x, ua, mp);
         perturb<M>(u, o, -eps, -1, S(0), ua);
         const S m = Model::cost(x, ua, mp);
-        cu[o] = (p - m) / (2 * eps);
+        cf[N + o] = (p - m) / (2 * eps);
         return;
       }
       o -= M;
@@ -245,8 +272,8 @@ struct Core {
       perturb<N>(x, i, -eps, j, -eps, xa);
       const S mm = fx(xa, u);
       const S v = (pp - mpv - pm + mm) / (4 * eps * eps);
-      cxx[i * N + j] = v;
-      cxx[j * N + i] = v;
+      cf[ix_cxx(i, j)] = v;
+      cf[ix_cxx(j, i)] = v;
       return;
     }
     o -= kNxx;
@@ -263,8 +290,8 @@ struct Core {
       perturb<M>(u, i, -eps, j, -eps, ua);
       const S mm = Model::cost(x, ua, mp);
       const S v = (pp - mpv - pm + mm) / (4 * eps * eps);
-      cuu[i * M + j] = v;
-      cuu[j * M + i] = v;
+      cf[ix_cuu(i, j)] = v;
+      cf[ix_cuu(j, i)] = v;
       return;
     }
     o -= kNuu;
@@ -275,10 +302,36 @@ struct Core {
       perturb<N>(x, i, -eps, -1, S(0), xm);
       perturb<M>(u, j, eps, -1, S(0), up);
       perturb<M>(u, j, -eps, -1, S(0), um);
-      cxu[i * M + j] =
+      const S v =
           (Model::cost(xp, up, mp) - Model::cost(xm, up, mp) - Model::cost(xp, um, mp) + Model::cost(xm, um, mp)) /
           (4 * (eps * eps));
+      cf[ix_cxu(i, j)] = v;
+      cf[ix_cux(j, i)] = v;
     }
+  }
+
+  /* closed-form cost derivatives of the model twin, scattered into the full layout (one lane) */
+  ILQR_HD void analytic_cost(const S *x, const S *u, bool terminal, S *cf) {
+    S cx[N], cu[M], cxx[N * N], cxu[N * M], cuu[M * M];
+    Model::cost_derivs(x, u, P.mp, terminal, cx, cu, cxx, cxu, cuu);
+#pragma unroll
+    for (int i = 0; i < N; i++) cf[i] = cx[i];
+#pragma unroll
+    for (int j = 0; j < M; j++) cf[N + j] = cu[j];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+#pragma unroll
+      for (int j = 0; j < N; j++) cf[ix_cxx(i, j)] = cxx[i * N + j];
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        cf[ix_cxu(i, j)] = cxu[i * M + j];
+        cf[ix_cux(j, i)] = cxu[i * M + j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++)
+#pragma unroll
+      for (int j = 0; j < M; j++) cf[ix_cuu(i, j)] = cuu[i * M + j];
   }
 
   /* get_dynamics_derivatives (+ get_cost_derivatives / get_cost_2nd_derivatives in FD mode) for the
@@ -319,8 +372,7 @@ struct Core {
           for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
 #pragma unroll
           for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
-          S *c = sl.C + (size_t)t * NC;
-          cost_stencil(o, false, x, u, c, c + N, c + N + M, c + N + M + N * N, c + N + M + N * N + N * M);
+          cost_stencil(o, false, x, u, sl.C + (size_t)t * NCF);
         });
       }
     }
@@ -330,16 +382,15 @@ struct Core {
   ILQR_HD void phase_terminal() {
     ex.lanes([&](int lane, Lane &) {
       if (CD == kCostFD) {
-        for (int o = lane; o < kStencilTerm; o += 32) cost_stencil(o, true, sc.x, sc.u, sc.cx, sc.cu, sc.cxx, sc.cxu, sc.cuu);
+        for (int o = lane; o < kStencilTerm; o += 32) cost_stencil(o, true, sc.x, sc.u, sc.Cf);
       } else if (lane == 0) {
-        S cu[M], cxu[N * M], cuu[M * M];
-        Model::cost_derivs(sc.x, sc.u, P.mp, true, sc.cx, cu, sc.cxx, cxu, cuu);
+        analytic_cost(sc.x, sc.u, true, sc.Cf);
       }
     });
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + N; e += 32) {
-        if (e < N * N) sc.Vxx[e] = sc.cxx[e];
-        else sc.Vx[e - N * N] = sc.cx[e - N * N];
+      for (int e = lane; e < N * NA; e += 32) {
+        const int r = e / NA, b = e % NA;
+        sc.Va[e] = (b < N) ? sc.Cf[ix_cxx(r, b < N ? b : 0)] : sc.Cf[r];
       }
     });
   }
@@ -347,89 +398,66 @@ struct Core {
   /* ---- backward pass -------------------------------------------------------------------- */
 
   /* One timestep of the backward recursion for tile entry tt; returns false when the boxQP reports
-   * failure (result < 1, src/ilqr_core.cpp:371).  On success sc.kc / sc.Kc hold k_i / K_i and
-   * sc.Vx / sc.Vxx the value function at i. */
-  ILQR_HD bool backward_step(int tt, S lam) {
+   * failure (result < 1, src/ilqr_core.cpp:371).  Every phase but the boxQP has a single code path:
+   * the value function is kept augmented, Va = [Vxx | Vx] (n x (n+1)), and so are the products
+   * that consume it, so Qx/Qu ride along as one more column of F^T Va and Vx as one more column
+   * of the Vxx update.  cf = cost derivatives of this timestep in the full layout. */
+  ILQR_HD bool backward_step(int tt, S lam, const S *cf) {
     const S *F = sc.Ft + tt * NM * N; /* F[j][r]: column j of [fx | fu] */
     const S *ut = sc.us + tt * M;
-    const S *cx, *cu, *cxx, *cxu, *cuu;
-    if constexpr (CD == kCostFD) {
-      cx = sc.Ct + tt * NC;
-      cu = cx + N;
-      cxx = cu + M;
-      cxu = cxx + N * N;
-      cuu = cxu + N * M;
-    } else {
-      cx = sc.cx;
-      cu = sc.cu;
-      cxx = sc.cxx;
-      cxu = sc.cxu;
-      cuu = sc.cuu;
-    }
-    /* W = F^T Vxx'  (the inner product of :361-363); closed-form cost derivatives ride on the last lane */
+    /* W = F^T [Vxx' | Vx']  (:359-363): column n gives Qx = cx + fx^T Vx', Qu = cu + fu^T Vx' */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < NM * N; e += 32) {
-        const int c = e / N, b = e % N;
-        S acc = 0;
+      for (int e = lane; e < NM * NA; e += 32) {
+        const int c = e / NA, b = e % NA;
+        Acc<S> acc;
 #pragma unroll
-        for (int r = 0; r < N; r++) acc += F[c * N + r] * sc.Vxx[r * N + b];
-        sc.W[e] = acc;
-      }
-      if (CD == kCostAnalytic && lane == 31)
-        Model::cost_derivs(sc.xs + tt * N, ut, P.mp, false, sc.cx, sc.cu, sc.cxx, sc.cxu, sc.cuu);
-    });
-    /* Qx, Qu (:359-360), Qxx, Qux, Quu and the regularised QuuF (:361-367); QuuF goes straight into the QP */
-    ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + M * N + M * M + NM; e += 32) {
-        if (e < N * N) {
-          const int a = e / N, b = e % N;
-          S acc = 0;
-#pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.W[a * N + r] * F[b * N + r];
-          sc.Qxx[e] = cxx[e] + acc;
-        } else if (e < N * N + M * N) {
-          const int q = e - N * N, a = q / N, b = q % N;
-          S acc = 0;
-#pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.W[(N + a) * N + r] * F[b * N + r];
-          sc.Qux[q] = cxu[b * M + a] + acc;
-        } else if (e < N * N + M * N + M * M) {
-          const int q = e - N * N - M * N, a = q / M, b = q % M;
-          S acc = 0;
-#pragma unroll
-          for (int r = 0; r < N; r++) acc += sc.W[(N + a) * N + r] * F[(N + b) * N + r];
-          sc.Quu[q] = cuu[q] + acc;
-          sc.qp.Q[q] = (cuu[q] + (a == b ? lam : S(0))) + acc;
-        } else {
-          const int c = e - N * N - M * N - M * M;
-          S acc = 0;
-#pragma unroll
-          for (int r = 0; r < N; r++) acc += F[c * N + r] * sc.Vx[r];
-          if (c < N) sc.Qx[c] = cx[c] + acc;
-          else sc.Qu[c - N] = cu[c - N] + acc;
+        for (int r = 0; r < N; r++) acc.add(F[c * N + r] * sc.Va[r * NA + b]);
+        sc.W[e] = acc.v;
+        if (b == N) {
+          const S q = cf[c] + acc.v;
+          if (c < N) sc.Qxa[c * NA + N] = q;
+          else sc.Qua[(c - N) * NA + N] = q;
         }
       }
     });
-    /* boxQP, gains, dV (:369-389) — one lane */
+    /* Q[c][d] = C[c][d] + sum_r W[c][r] F[d][r]: Qxx, Qux, Quu (:361-363) and the regularised QuuF (:367) */
+    ex.lanes([&](int lane, Lane &) {
+      for (int e = lane; e < NM * NM; e += 32) {
+        const int c = e / NM, d = e % NM;
+        Acc<S> acc;
+#pragma unroll
+        for (int r = 0; r < N; r++) acc.add(sc.W[c * NA + r] * F[d * N + r]);
+        const S cc = cf[NM + e];
+        const S q = cc + acc.v;
+        if (d < N) {
+          if (c < N) sc.Qxa[c * NA + d] = q;
+          else sc.Qua[(c - N) * NA + d] = q;
+        } else if (c >= N) {
+          sc.Quu[(c - N) * M + (d - N)] = q;
+          sc.qp.Q[(c - N) * M + (d - N)] = (cc + (c == d ? lam : S(0))) + acc.v;
+        }
+      }
+    });
+    /* boxQP, gains, dV (:369-389) — one lane; k / K go to the augmented gain Ka = [K | k] and to the tile */
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
       QPWork<M, S> &w = sc.qp;
 #pragma unroll
       for (int j = 0; j < M; j++) {
-        w.c[j] = sc.Qu[j];
+        w.c[j] = sc.Qua[j * NA + N];
         w.x0[j] = sc.kprev[j];
         w.lo[j] = P.u_min[j] - ut[j];
         w.hi[j] = P.u_max[j] - ut[j];
       }
       box_qp<M, S>(P.qp, w);
       if (w.result < 1) return;
+      for (int e = 0; e < M * NA; e++) sc.Ka[e] = 0;
 #pragma unroll
-      for (int j = 0; j < M; j++) sc.kc[j] = w.x[j];
-      for (int e = 0; e < M * N; e++) sc.Kc[e] = 0;
+      for (int j = 0; j < M; j++) sc.Ka[j * NA + N] = w.x[j];
       if constexpr (M == 1) {
         if (w.v_free[0]) {
 #pragma unroll
-          for (int b = 0; b < N; b++) sc.Kc[b] = (-w.Hinv[0]) * sc.Qux[b];
+          for (int b = 0; b < N; b++) sc.Ka[b] = (-w.Hinv[0]) * sc.Qua[b];
         }
       } else {
         const int r = w.r_dim;
@@ -440,79 +468,70 @@ struct Core {
           for (int a = 0; a < r && a < q; a++)
             for (int b = 0; b < N; b++) {
               S acc = 0;
-              for (int c = 0; c < r && c < q; c++) acc += (-w.Hinv[a * r + c]) * sc.Qux[w.idx[c] * N + b];
-              sc.Kc[w.idx[a] * N + b] = acc;
+              for (int c = 0; c < r && c < q; c++) acc += (-w.Hinv[a * r + c]) * sc.Qua[w.idx[c] * NA + b];
+              sc.Ka[w.idx[a] * NA + b] = acc;
             }
         }
       }
-      S a0 = 0; /* :388-389, unregularised Quu */
+      Acc<S> a0; /* :388-389, unregularised Quu */
 #pragma unroll
-      for (int j = 0; j < M; j++) a0 += sc.kc[j] * sc.Qu[j];
-      sc.st.dV0 += a0;
-      S a1 = 0;
+      for (int j = 0; j < M; j++) a0.add(sc.Ka[j * NA + N] * sc.Qua[j * NA + N]);
+      sc.st.dV0 += a0.v;
+      Acc<S> a1;
       S row[M];
 #pragma unroll
       for (int b = 0; b < M; b++) {
-        S acc = 0;
+        Acc<S> acc;
 #pragma unroll
-        for (int a = 0; a < M; a++) acc += (S(0.5) * sc.kc[a]) * sc.Quu[a * M + b];
-        row[b] = acc;
+        for (int a = 0; a < M; a++) acc.add((S(0.5) * sc.Ka[a * NA + N]) * sc.Quu[a * M + b]);
+        row[b] = acc.v;
       }
 #pragma unroll
-      for (int b = 0; b < M; b++) a1 += row[b] * sc.kc[b];
-      sc.st.dV1 += a1;
+      for (int b = 0; b < M; b++) a1.add(row[b] * sc.Ka[b * NA + N]);
+      sc.st.dV1 += a1.v;
+#pragma unroll
+      for (int j = 0; j < M; j++) { /* :396-397, and the warm start of the next boxQP (:369) */
+        sc.kprev[j] = sc.Ka[j * NA + N];
+        sc.k[tt * M + j] = sc.Ka[j * NA + N];
+#pragma unroll
+        for (int b = 0; b < N; b++) sc.K[(tt * M + j) * N + b] = sc.Ka[j * NA + b];
+      }
     });
     if (sc.qp.result < 1) return false;
-    /* Vx, Vxx before symmetrisation (:391-392) */
+    /* [Vxx | Vx] before symmetrisation (:391-392): column b < n is Vxx[:, b], column n is Vx */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + N; e += 32) {
-        const int a = (e < N * N) ? e / N : e - N * N;
+      for (int e = lane; e < N * NA; e += 32) {
+        const int a = e / NA, b = e % NA;
         S ktq[M]; /* row a of K^T Quu */
 #pragma unroll
-        for (int b = 0; b < M; b++) {
-          S acc = 0;
+        for (int bb = 0; bb < M; bb++) {
+          Acc<S> acc;
 #pragma unroll
-          for (int c = 0; c < M; c++) acc += sc.Kc[c * N + a] * sc.Quu[c * M + b];
-          ktq[b] = acc;
+          for (int c = 0; c < M; c++) acc.add(sc.Ka[c * NA + a] * sc.Quu[c * M + bb]);
+          ktq[bb] = acc.v;
         }
-        if (e < N * N) {
-          const int b = e % N;
-          S t1 = 0, t2 = 0, t3 = 0;
+        Acc<S> t1, t2, t3;
 #pragma unroll
-          for (int c = 0; c < M; c++) t1 += ktq[c] * sc.Kc[c * N + b];
+        for (int c = 0; c < M; c++) t1.add(ktq[c] * sc.Ka[c * NA + b]);
 #pragma unroll
-          for (int c = 0; c < M; c++) t2 += sc.Kc[c * N + a] * sc.Qux[c * N + b];
+        for (int c = 0; c < M; c++) t2.add(sc.Ka[c * NA + a] * sc.Qua[c * NA + b]);
 #pragma unroll
-          for (int c = 0; c < M; c++) t3 += sc.Qux[c * N + a] * sc.Kc[c * N + b];
-          sc.Vtmp[e] = sc.Qxx[e] + t1 + t2 + t3;
-        } else {
-          S t1 = 0, t2 = 0, t3 = 0;
-#pragma unroll
-          for (int c = 0; c < M; c++) t1 += ktq[c] * sc.kc[c];
-#pragma unroll
-          for (int c = 0; c < M; c++) t2 += sc.Kc[c * N + a] * sc.Qu[c];
-#pragma unroll
-          for (int c = 0; c < M; c++) t3 += sc.Qux[c * N + a] * sc.kc[c];
-          sc.Vxn[a] = sc.Qx[a] + t1 + t2 + t3;
-        }
+        for (int c = 0; c < M; c++) t3.add(sc.Qua[c * NA + a] * sc.Ka[c * NA + b]);
+        sc.Vt[e] = sc.Qxa[e] + t1.v + t2.v + t3.v;
       }
     });
-    /* symmetrise (:393), roll the value function, remember k for the next warm start, stage k / K (:396-397) */
+    /* symmetrise (:393) and roll the value function; the closed-form cost derivatives of the next
+     * timestep (tt - 1) are prepared on the last lane */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + N + M + M * N + M; e += 32) {
-        if (e < N * N) {
-          const int a = e / N, b = e % N;
-          sc.Vxx[e] = S(0.5) * (sc.Vtmp[a * N + b] + sc.Vtmp[b * N + a]);
-        } else if (e < N * N + N) {
-          sc.Vx[e - N * N] = sc.Vxn[e - N * N];
-        } else if (e < N * N + N + M) {
-          sc.kprev[e - N * N - N] = sc.kc[e - N * N - N];
-        } else if (e < N * N + N + M + M * N) {
-          sc.K[tt * M * N + e - (N * N + N + M)] = sc.Kc[e - (N * N + N + M)];
-        } else {
-          sc.k[tt * M + e - (N * N + N + M + M * N)] = sc.kc[e - (N * N + N + M + M * N)];
-        }
+      for (int e = lane; e < N * NA; e += 32) {
+        const int a = e / NA, b = e % NA;
+        const int bt = (b < N) ? b : a; /* column n (Vx) is copied: 0.5 * (v + v) == v exactly */
+        const int at = (b < N) ? a : N;
+        const S v1 = sc.Vt[a * NA + b];
+        const S v2 = (b < N) ? sc.Vt[bt * NA + at] : v1;
+        sc.Va[e] = S(0.5) * (v1 + v2);
       }
+      if (CD == kCostAnalytic && lane == 31 && tt > 0) analytic_cost(sc.xs + (tt - 1) * N, sc.us + (tt - 1) * M, false, sc.Cf);
     });
     return true;
   }
@@ -542,12 +561,18 @@ struct Core {
         for (int e = lane; e < cnt * M; e += 32) sc.us[e] = tr.us[t0 * M + e];
         for (int e = lane; e < cnt * NM * N; e += 32) sc.Ft[e] = ld_fresh(sl.F + (size_t)t0 * NM * N + e);
         if constexpr (CD == kCostFD) {
-          for (int e = lane; e < cnt * NC; e += 32) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NC + e);
+          for (int e = lane; e < cnt * NCF; e += 32) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NCF + e);
         }
       });
+      if constexpr (CD == kCostAnalytic) { /* cost derivatives of the tile's first timestep (the rest are prepared step by step) */
+        ex.lanes([&](int lane, Lane &) {
+          if (lane == 0) analytic_cost(sc.xs + (cnt - 1) * N, sc.us + (cnt - 1) * M, false, sc.Cf);
+        });
+      }
       int first_done = 0; /* tile entries [first_done, cnt) hold finished k / K */
       for (int tt = cnt - 1; tt >= 0; tt--) {
-        if (!backward_step(tt, lam)) { /* the steps above this one have already written their k, K (:396-397) */
+        const S *cf = (CD == kCostFD) ? sc.Ct + tt * NCF : sc.Cf;
+        if (!backward_step(tt, lam, cf)) { /* the steps above this one have already written their k, K (:396-397) */
           diverged_at = t0 + tt;
           first_done = tt + 1;
           break;
@@ -563,9 +588,10 @@ struct Core {
     if (diverged_at >= 0) return diverged_at;
     /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * N + N; e += 32) {
-        if (e < N * N) tr.Vxx0[e] = sc.Vxx[e];
-        else tr.Vx0[e - N * N] = sc.Vx[e - N * N];
+      for (int e = lane; e < N * NA; e += 32) {
+        const int r = e / NA, b = e % NA;
+        if (b < N) tr.Vxx0[r * N + b] = sc.Va[e];
+        else tr.Vx0[r] = sc.Va[e];
       }
     });
     return 0;
@@ -611,10 +637,10 @@ struct Core {
       S v = ubar[j];
       if (mode == kRollClosed) v = ubar[j] + kt[j] * alpha; /* :188-190 */
       if (mode != kRollOpen) {                              /* :316 */
-        S a = 0;
+        Acc<S> a;
 #pragma unroll
-        for (int i = 0; i < N; i++) a += Kt[j * N + i] * (L.x[i] - xhat[i]);
-        v += a;
+        for (int i = 0; i < N; i++) a.add(Kt[j * N + i] * (L.x[i] - xhat[i]));
+        v += a.v;
       }
       L.uc[j] = v;
     }

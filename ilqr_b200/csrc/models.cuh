@@ -169,8 +169,13 @@ struct DoubleIntegrator {
 };
 
 /* Model::integrate_dynamics, include/model.h:12-15: x + dynamics(x, u) * dt */
+#if defined(__CUDACC__) && defined(ILQR_NOINLINE_DYN)
+#define ILQR_HD_DYN __host__ __device__ __noinline__
+#else
+#define ILQR_HD_DYN ILQR_HD
+#endif
 template <class Model, typename S>
-ILQR_HD void integrate(const S *x, const S *u, const S *mp, S dt, S *x1) {
+ILQR_HD_DYN void integrate(const S *x, const S *u, const S *mp, S dt, S *x1) {
   S dx[Model::N];
   Model::dynamics(x, u, mp, dx);
 #pragma unroll

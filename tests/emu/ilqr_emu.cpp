@@ -84,7 +84,7 @@ struct Emu : EmuBase {
     Vxx0.assign(N * N, 0);
     gterm.assign(T, 0);
     bufF.assign((size_t)T * (N + M) * N, 0);
-    bufC.assign((size_t)T * Scratch<N, M, S, CD>::NC, 0);
+    bufC.assign((size_t)T * Scratch<N, M, S, CD>::NCF, 0);
     candX.assign((size_t)P.n_alpha * T * N, 0);
     candU.assign((size_t)P.n_alpha * T * M, 0);
     for (int i = 0; i < N; i++) x0[i] = S(x0_[i]);
