@@ -57,7 +57,7 @@ struct KArgs {
 /* shared memory of one warp: its scratch, then T gradient-norm terms; 16-byte granules */
 template <class Sc, typename S>
 __host__ __device__ inline size_t warp_smem_bytes(int T) {
-  return (sizeof(Sc) + (size_t)T * sizeof(S) + 15) & ~(size_t)15;
+  return (sizeof(Sc) + (size_t)T * sizeof(S) + sizeof(unsigned long long) + 15) & ~(size_t)15;
 }
 
 template <class Model, typename S, int CD>
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) ilqr_warp_kernel(co
   sl.gterm = reinterpret_cast<S *>(mine + sizeof(Sc));
   WarpExec<N, M, S> ex;
   ex.lane = threadIdx.x & 31;
+  ex.init_barrier(reinterpret_cast<unsigned long long *>(mine + per_warp - 16));
   for (;;) {
     unsigned long long b = 0;
     if (ex.lane == 0) b = atomicAdd(a.queue, 1ULL);
@@ -218,6 +219,8 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
     }
     h->slots = slots;
   }
+  a.P.bulk_f = ((size_t)h->slotF % 16 == 0) && (((size_t)h->desc.T * (N + M) * N * sizeof(S)) % 16 == 0) &&
+               (((size_t)kTileB * (N + M) * N * sizeof(S)) % 16 == 0);
   a.slotF = (S *)h->slotF;
   a.slotC = (S *)h->slotC;
   a.slotCandX = (S *)h->slotCandX;

@@ -65,6 +65,7 @@ struct SolveParams {
   S u_min[4], u_max[4];
   S mp[16];
   QPParams<S> qp;
+  int bulk_f; /* host-set: every tile of the per-warp Jacobian buffer starts 16-byte aligned (bulk copy allowed) */
 };
 
 /* per-trajectory solver state that survives between launches (one slot per trajectory) */
@@ -105,7 +106,7 @@ struct Scratch {
   static constexpr int NCF = NM + NM * NM;      /* cost derivatives of one timestep, full layout (Core::cost_stencil) */
   /* staged tiles: rollouts use kTile timesteps, the backward pass the first kTileB of the same arrays */
   S xs[kTile * N], us[kTile * M], K[kTile * M * N], k[kTile * M];
-  S Ft[kTileB * NM * N];                     /* backward: Jacobian columns of the tile                 */
+  alignas(16) S Ft[kTileB * NM * N];         /* backward: Jacobian columns of the tile (bulk-copy target) */
   S Ct[CD == kCostFD ? kTileB * NCF : 1];    /* backward: FD cost derivatives of the tile (full layout) */
   /* one timestep */
   S x[N], u[M];         /* xs[T] and a zero control for the terminal derivatives */
@@ -132,19 +133,72 @@ struct LaneRegs {
 };
 
 #if defined(__CUDACC__)
-/* device: the calling thread is one lane; a phase ends with a warp barrier */
+/* device: the calling thread is one lane; a phase ends with a warp barrier.
+ *
+ * stage_issue / stage_wait move one contiguous tile global -> shared with the 1-D bulk form of TMA
+ * (cp.async.bulk, completion counted in bytes on the warp's mbarrier): one instruction on lane 0 instead of
+ * five load/store pairs on every lane for the 1.25 KB Jacobian tile, and the copy runs while the lanes
+ * stage the small xs / us tiles themselves.  Unaligned tiles fall back to a coalesced lane copy.  (Staging
+ * EVERY tile this way with double buffering and prefetch was measured and is slower at this occupancy:
+ * profiles/experiments/.) */
 template <int N, int M, typename S>
 struct WarpExec {
   LaneRegs<N, M, S> regs;
   int lane;
+  unsigned bar;         /* shared-window address of the warp's mbarrier */
+  unsigned phase = 0;   /* bit 0: parity to wait for; bit 1: a bulk copy is outstanding */
+
   template <class Fn>
   __device__ __forceinline__ void lanes(Fn fn) {
     fn(lane, regs);
     __syncwarp();
   }
+  __device__ __forceinline__ static unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+  __device__ __forceinline__ void init_barrier(unsigned long long *b) {
+    bar = s32(b);
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  /* global writes of this warp (generic proxy) that a later bulk copy (async proxy) will read */
+  __device__ __forceinline__ void publish() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+  }
+  __device__ __forceinline__ void stage_issue(S *dst, const S *src, int count, bool aligned) {
+    const unsigned bytes = (unsigned)count * (unsigned)sizeof(S);
+    if (aligned && (bytes & 15u) == 0) {
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* earlier generic reads of the destination */
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+      }
+      phase |= 2u;
+    } else {
+      for (int e = lane; e < count; e += 32) dst[e] = src[e];
+    }
+  }
+  __device__ __forceinline__ void stage_wait() {
+    if (phase & 2u) {
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(phase & 1u)
+            : "memory");
+      }
+      phase = (phase ^ 1u) & 1u;
+    }
+    __syncwarp();
+  }
 };
 #endif
-/* host (tests only): run the phase for lane 0..31 in turn */
+/* host (tests only): run the phase for lane 0..31 in turn; a staged tile is a plain copy */
 template <int N, int M, typename S>
 struct HostExec {
   LaneRegs<N, M, S> regs[32];
@@ -152,6 +206,11 @@ struct HostExec {
   void lanes(Fn fn) {
     for (int l = 0; l < 32; l++) fn(l, regs[l]);
   }
+  void publish() {}
+  void stage_issue(S *dst, const S *src, int count, bool) {
+    for (int e = 0; e < count; e++) dst[e] = src[e];
+  }
+  void stage_wait() {}
 };
 
 /* Accumulates products in index order.  The reference's sums start from zero (Eigen zero-initialises, the
@@ -376,6 +435,7 @@ struct Core {
         });
       }
     }
+    ex.publish(); /* F is read by the backward pass's bulk copies */
   }
 
   /* Vx[T] = cx[T], Vxx[T] = cxx[T]  (src/ilqr_core.cpp:353-354) from sc.x = xs[T] */
@@ -556,14 +616,15 @@ struct Core {
     for (int ti = (T - 1) / kTileB; ti >= 0 && diverged_at < 0; ti--) {
       const int t0 = ti * kTileB;
       const int cnt = (T - t0 < kTileB) ? T - t0 : kTileB;
+      ex.stage_issue(sc.Ft, sl.F + (size_t)t0 * NM * N, cnt * NM * N, P.bulk_f != 0);
       ex.lanes([&](int lane, Lane &) {
         for (int e = lane; e < cnt * N; e += 32) sc.xs[e] = tr.xs[t0 * N + e];
         for (int e = lane; e < cnt * M; e += 32) sc.us[e] = tr.us[t0 * M + e];
-        for (int e = lane; e < cnt * NM * N; e += 32) sc.Ft[e] = ld_fresh(sl.F + (size_t)t0 * NM * N + e);
         if constexpr (CD == kCostFD) {
           for (int e = lane; e < cnt * NCF; e += 32) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NCF + e);
         }
       });
+      ex.stage_wait();
       if constexpr (CD == kCostAnalytic) { /* cost derivatives of the tile's first timestep (the rest are prepared step by step) */
         ex.lanes([&](int lane, Lane &) {
           if (lane == 0) analytic_cost(sc.xs + (cnt - 1) * N, sc.us + (cnt - 1) * M, false, sc.Cf);
