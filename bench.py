@@ -318,17 +318,18 @@ def ours_arm(args, cfg):
     # ---- timed region 1: resident inputs ------------------------------------------------------
     barrier()
     wall0 = time.perf_counter()
-    evs, trips, acc, rej = [], 0, 0, 0
+    evs, trips, acc, rej, launches = [], 0, 0, 0, 0
     for _ in range(args.steps):
         do_flush()
+        l0 = solver.launch_count
         evs.append(step_resident())
+        launches += solver.launch_count - l0  # init_traj kernel + solve kernel + cost gather, per step
         solver.sync()
         trips += int(solver.get("iters").sum())
         acc += int(solver.get("n_accept").sum())
         rej += int(solver.get("n_reject").sum())
     barrier()
     wall_resident = time.perf_counter() - wall0
-    launches = solver.launch_count - launches0
     step_ms = [e[0].elapsed_time(e[3]) for e in evs]
     solve_ms = [e[1].elapsed_time(e[2]) for e in evs]
     # ---- timed region 2: end to end ---------------------------------------------------------------
@@ -343,9 +344,24 @@ def ours_arm(args, cfg):
     barrier()
     e2e_ms = [e[0].elapsed_time(e[1]) for e in evs2]
     clocks = sampler.stop() if rank == 0 else None
+    # ---- extra (not the headline): fixed-N mode, every instance runs exactly N trips, no ragged tail
+    N_FIXED = 15
+    fixed_ms, fixed_trips = [], 0
+    for _ in range(min(args.steps, 3)):
+        do_flush()
+        with torch.cuda.stream(stream):
+            solver.set_initial_device(x0_d.data_ptr(), u0_d.data_ptr())
+            f0, f1 = ev(), ev()
+            f0.record()
+            solver.iterate(N_FIXED)
+            f1.record()
+        solver.sync()
+        fixed_ms.append(f0.elapsed_time(f1))
+        fixed_trips += int(solver.get("iters").sum())
 
     # whole-job numbers: sum of trips over ranks / max time over ranks
-    t_res, cnt = shard.reduce_step_stats([sum(step_ms), sum(e2e_ms), sum(solve_ms)], [trips, trips_e2e, acc, rej], dev)
+    t_res, cnt = shard.reduce_step_stats([sum(step_ms), sum(e2e_ms), sum(solve_ms), sum(fixed_ms)],
+                                         [trips, trips_e2e, acc, rej, fixed_trips], dev)
     if rank == 0:
         value = cnt[0] / (t_res[0] * 1e-3)
         e2e = cnt[1] / (t_res[1] * 1e-3)
@@ -353,6 +369,12 @@ def ours_arm(args, cfg):
         alg_bytes_per_launch = (cnt[2] * b_acc + cnt[3] * b_rej) / world / args.steps  # per GPU per solve launch
         solve_s = t_res[2] * 1e-3 / args.steps
         achieved = alg_bytes_per_launch / solve_s / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes of ONE solve launch, from an ncu --set full capture
+        if os.path.exists(tpath) and world == 1:
+            tj = json.load(open(tpath)).get(args.config)
+            if tj and tj.get("batch") == B:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
@@ -366,13 +388,15 @@ def ours_arm(args, cfg):
                        "step": "init_traj + generate_trajectory to termination for every instance; one NCCL gather of final costs when N>1",
                        "l2": "512 MiB buffer written between timed steps (L2 flush)",
                        "trips_per_step": cnt[0] / args.steps, "accepted": cnt[2] / args.steps, "rejected": cnt[3] / args.steps,
-                       "wall_s_resident_region": wall_resident},
+                       "wall_s_resident_region": wall_resident,
+                       "fixed_n_mode": {"trips_per_instance": N_FIXED, "value": cnt[4] / (t_res[3] * 1e-3), "unit": UNIT,
+                                        "note": "every instance runs exactly N trips in one launch: the kernel's rate without the ragged-termination tail"}},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": t_res[1] / args.steps,
                     "h2d_bytes_per_step": int(world * (x0_h.numel() + u0_h.numel()) * 8),
                     "d2h_bytes_per_step": int(world * (B * 8 + B * 4))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "ilqr_warp_kernel<Acrobot,double,%s> (op_iterate)" % cfg["cost_deriv"],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel_ms": solve_s * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "note": "fp64 finite-difference + boxQP arithmetic bounds this kernel (SURVEY.md §8d secondary ceiling), not HBM"},

@@ -128,7 +128,6 @@ struct Scratch {
 template <int N, int M, typename S>
 struct LaneRegs {
   S x[N];
-  S uc[M];
   S cost;
 };
 
@@ -691,8 +690,9 @@ struct Core {
 
   /* ---- rollouts ------------------------------------------------------------------------- */
 
-  /* one step of iLQR::forward_pass (:314-326) for one lane; the applied control is left in L.uc */
-  ILQR_HD void rollout_step(Lane &L, const S *xhat, const S *ubar, const S *kt, const S *Kt, S alpha, int mode) {
+  /* one step of iLQR::forward_pass (:314-326) for one lane: x, cost are the lane's running state (kept in
+   * registers by the callers' tile loops), uc receives the applied control */
+  ILQR_HD void rollout_step(S *x, S &cost, S *uc, const S *xhat, const S *ubar, const S *kt, const S *Kt, S alpha, int mode) {
 #pragma unroll
     for (int j = 0; j < M; j++) {
       S v = ubar[j];
@@ -700,16 +700,16 @@ struct Core {
       if (mode != kRollOpen) {                              /* :316 */
         Acc<S> a;
 #pragma unroll
-        for (int i = 0; i < N; i++) a.add(Kt[j * N + i] * (L.x[i] - xhat[i]));
+        for (int i = 0; i < N; i++) a.add(Kt[j * N + i] * (x[i] - xhat[i]));
         v += a.v;
       }
-      L.uc[j] = v;
+      uc[j] = v;
     }
-    L.cost += Model::cost(L.x, L.uc, P.mp); /* :324 */
+    cost += Model::cost(x, uc, P.mp); /* :324 */
     S x1[N];
-    integrate<Model, S>(L.x, L.uc, P.mp, P.dt, x1); /* :325 */
+    integrate<Model, S>(x, uc, P.mp, P.dt, x1); /* :325 */
 #pragma unroll
-    for (int i = 0; i < N; i++) L.x[i] = x1[i];
+    for (int i = 0; i < N; i++) x[i] = x1[i];
   }
 
   ILQR_HD void load_forward_tile(int t0, int cnt, int mode) {
@@ -741,13 +741,19 @@ struct Core {
         const S alpha = P.alpha[lane];
         S *cx = sl.cand_x + ((size_t)lane * T + t0) * N;
         S *cu = sl.cand_u + ((size_t)lane * T + t0) * M;
+        S x[N], uc[M], cost = L.cost; /* the tile runs on register copies of the lane state */
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = L.x[i];
         for (int tt = 0; tt < cnt; tt++) {
-          rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, kRollClosed);
+          rollout_step(x, cost, uc, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, kRollClosed);
 #pragma unroll
-          for (int j = 0; j < M; j++) cu[tt * M + j] = L.uc[j];
+          for (int j = 0; j < M; j++) cu[tt * M + j] = uc[j];
 #pragma unroll
-          for (int i = 0; i < N; i++) cx[tt * N + i] = L.x[i];
+          for (int i = 0; i < N; i++) cx[tt * N + i] = x[i];
         }
+#pragma unroll
+        for (int i = 0; i < N; i++) L.x[i] = x[i];
+        L.cost = cost;
       });
     }
     ex.lanes([&](int lane, Lane &L) {
@@ -784,13 +790,19 @@ struct Core {
       load_forward_tile(t0, cnt, mode);
       ex.lanes([&](int lane, Lane &L) {
         if (lane != 0) return;
+        S x[N], uc[M], cost = L.cost;
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = L.x[i];
         for (int tt = 0; tt < cnt; tt++) {
 #pragma unroll
-          for (int i = 0; i < N; i++) tr.xs[(t0 + tt) * N + i] = L.x[i];
-          rollout_step(L, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, mode);
+          for (int i = 0; i < N; i++) tr.xs[(t0 + tt) * N + i] = x[i];
+          rollout_step(x, cost, uc, sc.xs + tt * N, sc.us + tt * M, sc.k + tt * M, sc.K + tt * M * N, alpha, mode);
 #pragma unroll
-          for (int j = 0; j < M; j++) tr.us[(t0 + tt) * M + j] = L.uc[j];
+          for (int j = 0; j < M; j++) tr.us[(t0 + tt) * M + j] = uc[j];
         }
+#pragma unroll
+        for (int i = 0; i < N; i++) L.x[i] = x[i];
+        L.cost = cost;
       });
     }
     ex.lanes([&](int lane, Lane &L) {
