@@ -411,7 +411,12 @@ def ours_arm(args, cfg):
             line["cpu_baseline"] = {"value": it / wall, "unit": UNIT, "cores": used, "kind": kind,
                                     "sample": "first %d of %d instances, solved to termination, %d forked workers, %.1f s wall"
                                               % (n_sample, B, used, wall),
-                                    "max_rel_cost_diff_vs_gpu": float(rel.max())}
+                                    # same instances, GPU vs the reference's own solve.  NB the reference always takes its cost
+                                    # derivatives by finite differences; configs[1] asks the GPU for the closed forms, a ~5e-10
+                                    # perturbation that (like any other) flips a line-search branch in a few % of instances
+                                    "terminal_cost_vs_gpu": {"median_rel_diff": float(np.median(rel)),
+                                                             "frac_within_1e-6": float((rel <= 1e-6).mean()),
+                                                             "frac_within_1e-3": float((rel <= 1e-3).mean())}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -425,7 +430,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override instances per GPU")
-    ap.add_argument("--cpu-per-core", type=int, default=48, help="CPU baseline: instances per host core in the sample")
+    ap.add_argument("--cpu-per-core", type=int, default=128, help="CPU baseline: instances per host core in the sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -421,3 +421,67 @@ def test_host_batch_entry_point(tmp_path, golden_solver):
     assert ok >= 4                                                            # FD-cost mode, bifurcations tolerated
     single = lines[6]
     assert abs(float(single[3]) - float(lines[0][3])) <= 1e-9 * abs(float(lines[0][3]))  # single API == batch entry 0
+
+
+# ---------------------------------------------------------------------------------------------
+# edge shapes and non-default parameters: GPU == kernel source on the CPU, bit for bit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model,T,B,dt", [(abi.MODEL_ACROBOT, 1, 1, 0.02), (abi.MODEL_ACROBOT, 5, 3, 0.02),
+                                          (abi.MODEL_ACROBOT, 9, 7, 0.05), (abi.MODEL_ACROBOT, 33, 5, 0.02),
+                                          (abi.MODEL_DOUBLE_INTEGRATOR, 7, 3, 0.05), (abi.MODEL_DOUBLE_INTEGRATOR, 17, 2, 0.1)])
+def test_edge_shapes_bit_exact(model, T, B, dt):
+    """horizons shorter than a tile, not a multiple of a tile (so unaligned tiles take the lane-copy path),
+    batches that do not fill a CTA"""
+    n, m = abi.MODEL_DIMS[model]
+    x0, u0 = make_inputs(4242, B, T, n, m, canonical_first=False)
+    kw = dict(goal=[0.5, -0.5, 0.0, 0.0]) if model == abi.MODEL_DOUBLE_INTEGRATOR else {}
+    s = BatchILQR(model, T=T, B=B, dt=dt, **kw)
+    s.generate_trajectory(x0, u0)
+    g = gpu_snap(s)
+    for b in range(B):
+        e = E.EmuSolver(model, dt, **kw)
+        e.init(x0[b], u0[b])
+        e.iterate(1000)
+        r = snap(e)
+        for f in g:
+            assert np.array_equal(np.asarray(g[f][b]), np.asarray(r[f])), (b, f)
+
+
+def test_non_default_parameters_bit_exact():
+    """every tunable of ilqr_params reaches the kernels (shorter alpha table, other eps / tolerances / lambda schedule)"""
+    p = abi.default_params()
+    p.max_iter, p.n_alpha = 9, 5
+    for i, a in enumerate((1.0, 0.3, 0.09, 0.027, 0.0081)):
+        p.alpha[i] = a
+    p.fd_eps, p.lambda_init, p.lambda_factor, p.tol_fun, p.z_min = 5e-4, 2.0, 2.0, 1e-4, 0.05
+    p.qp_armijo, p.qp_step_dec, p.qp_clamp_tol = 0.2, 0.5, 1e-3
+    B, T = 6, 60
+    x0, u0 = make_inputs(99, B, T, 4, 1, canonical_first=False)
+    kw = dict(u_min=[-2.0], u_max=[2.5])
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, params=p, **kw)
+    s.generate_trajectory(x0, u0)
+    g = gpu_snap(s)
+    assert (g["trips"] <= 9).all()
+    for b in range(B):
+        e = E.EmuSolver(abi.MODEL_ACROBOT, 0.02, params=p, **kw)
+        e.init(x0[b], u0[b])
+        e.iterate(1000)
+        r = snap(e)
+        o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, params=p, **kw)
+        o.init(x0[b], u0[b])
+        o.iterate(1000)
+        for f in g:
+            assert np.array_equal(np.asarray(g[f][b]), np.asarray(r[f])), (b, f)
+        assert abs(o.cost - g["cost"][b]) <= 1e-6 * abs(o.cost)
+
+
+def test_f32_config3_shape():
+    """BASELINE configs[2] arithmetic at its horizon (T = 500, f32, FD fx/fu, analytic cost derivatives), reduced batch"""
+    B, T = 2048, 500
+    x0, u0 = make_inputs(12345, B, T, 4, 1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, dtype=abi.F32, cost_deriv=abi.COST_ANALYTIC)
+    c0 = s.init_traj(x0, u0)
+    s.iterate(8)
+    c1 = s.get("cost")
+    assert np.isfinite(c1).all() and (c1 <= c0).all() and np.median(c1 / c0) < 0.7
+    assert (s.get("iters") == 8).all()
