@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -60,30 +61,43 @@ __host__ __device__ inline size_t warp_smem_bytes(int T) {
   return (sizeof(Sc) + (size_t)T * sizeof(S) + sizeof(unsigned long long) + 15) & ~(size_t)15;
 }
 
-template <class Model, typename S, int CD>
-__global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) ilqr_warp_kernel(const __grid_constant__ KArgs<S> a) {
+/* G = lanes per trajectory: 32 (one trajectory per warp) or 16 (two per warp; used for batches large enough
+ * to fill the machine that way).  With G = 16 the two halves of a warp run the SAME code on their own
+ * trajectories, so the phases where at most 16 lanes have work — the boxQP lane and the 11 line-search
+ * candidates, more than half of all instructions — are issued once for two trajectories.  The iterate
+ * operation advances both halves one loop trip at a time so they stay in lockstep; a half whose trajectory
+ * has terminated pulls the next instance from the queue at the trip boundary. */
+template <class Model, typename S, int CD, int G>
+__global__ void __launch_bounds__(kThreads, G == 32 ? ILQR_MIN_BLOCKS : 4) ilqr_warp_kernel(const __grid_constant__ KArgs<S> a) {
   constexpr int N = Model::N, M = Model::M;
-  using Sc = typename Core<Model, S, CD, WarpExec<N, M, S>>::Sc;
+  constexpr int kGroupsPerCta = kThreads / G;
+  using Ex = WarpExec<N, M, S, G>;
+  using CoreT = Core<Model, S, CD, Ex>;
+  using Sc = typename CoreT::Sc;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const size_t per_warp = warp_smem_bytes<Sc, S>(a.P.T);
-  unsigned char *mine = smem_raw + (threadIdx.x >> 5) * per_warp;
+  const size_t per_group = warp_smem_bytes<Sc, S>(a.P.T);
+  const int group = threadIdx.x / G;
+  unsigned char *mine = smem_raw + group * per_group;
   Sc &sc = *reinterpret_cast<Sc *>(mine);
   const int T = a.P.T;
-  const size_t slot = (size_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const size_t slot = (size_t)blockIdx.x * kGroupsPerCta + group;
   SlotPtrs<S> sl;
   sl.F = a.slotF + slot * (size_t)T * (N + M) * N;
   sl.C = a.slotC ? a.slotC + slot * (size_t)T * Sc::NCF : nullptr;
   sl.cand_x = a.slotCandX + slot * (size_t)a.P.n_alpha * T * N;
   sl.cand_u = a.slotCandU + slot * (size_t)a.P.n_alpha * T * M;
   sl.gterm = reinterpret_cast<S *>(mine + sizeof(Sc));
-  WarpExec<N, M, S> ex;
-  ex.lane = threadIdx.x & 31;
-  ex.init_barrier(reinterpret_cast<unsigned long long *>(mine + per_warp - 16));
-  for (;;) {
+  Ex ex;
+  ex.lane = threadIdx.x & (G - 1);
+  const int leader = (threadIdx.x & 31) & ~(G - 1); /* first lane of this group within the warp */
+  ex.mask = G == 32 ? 0xffffffffu : (0xffffu << leader);
+  ex.init_barrier(reinterpret_cast<unsigned long long *>(mine + per_group - 16));
+  auto next_instance = [&]() -> long long {
     unsigned long long b = 0;
     if (ex.lane == 0) b = atomicAdd(a.queue, 1ULL);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if ((long long)b >= a.B) break;
+    return (long long)__shfl_sync(ex.mask, b, leader);
+  };
+  auto pointers = [&](long long b) {
     TrajPtrs<S> tr;
     tr.x0 = a.x0 + b * N;
     tr.xs = a.xs + b * (size_t)(T + 1) * N;
@@ -93,16 +107,43 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) ilqr_warp_kernel(co
     tr.Vx0 = a.Vx0 + b * N;
     tr.Vxx0 = a.Vxx0 + b * N * N;
     tr.st = a.st + b;
-    Core<Model, S, CD, WarpExec<N, M, S>> core(a.P, sc, ex, tr, sl);
-    switch (a.op) {
-      case kOpInit: core.op_init(); break;
-      case kOpWarm: core.op_warm_start(); break;
-      case kOpIterate: core.op_iterate(a.n_iters); break;
-      case kOpBackwardOnce: core.op_backward_once(a.scalar); break;
-      case kOpRolloutOnce: core.op_rollout_once(a.scalar); break;
-      default: break;
+    return tr;
+  };
+  CoreT core(a.P, sc, ex, pointers(0), sl);
+  if (G == 32 || a.op != kOpIterate) {
+    for (;;) {
+      const long long b = next_instance();
+      if (b >= a.B) break;
+      core.tr = pointers(b);
+      switch (a.op) {
+        case kOpInit: core.op_init(); break;
+        case kOpWarm: core.op_warm_start(); break;
+        case kOpIterate: core.op_iterate(a.n_iters); break;
+        case kOpBackwardOnce: core.op_backward_once(a.scalar); break;
+        case kOpRolloutOnce: core.op_rollout_once(a.scalar); break;
+        default: break;
+      }
+      __syncwarp(ex.mask);
     }
-    __syncwarp();
+  } else {
+    bool has = false, drained = false;
+    for (;;) {
+      if (!has && !drained) {
+        const long long b = next_instance();
+        if (b < a.B) {
+          core.tr = pointers(b);
+          core.iterate_begin(a.n_iters);
+          has = true;
+        } else {
+          drained = true;
+        }
+      }
+      if (!__any_sync(0xffffffffu, has)) break; /* both halves meet here once per trip */
+      if (has && !core.iterate_trip()) {
+        core.iterate_end();
+        has = false;
+      }
+    }
   }
 }
 
@@ -144,6 +185,7 @@ struct ilqr_handle {
        *st = nullptr, *tmp = nullptr;
   void *slotF = nullptr, *slotC = nullptr, *slotCandX = nullptr, *slotCandU = nullptr; /* per resident warp */
   long long slots = 0;
+  int lanes = 0; /* 0: choose by batch size; 16 / 32: forced (environment ILQR_B200_LANES, for experiments and tests) */
   unsigned long long *queue = nullptr;
   int num_sms = 0;
   int64_t launches = 0;
@@ -178,9 +220,10 @@ int fail(ilqr_handle *h, int code, const std::string &msg) {
       return fail(h, ILQR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
   } while (0)
 
-template <class Model, typename S, int CD>
+template <class Model, typename S, int CD, int G>
 int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
   constexpr int N = Model::N, M = Model::M;
+  constexpr int kGroupsPerCta = kThreads / G;
   KArgs<S> a;
   if (make_solve_params<S>(h->desc, &a.P) != 0) return fail(h, ILQR_E_INVALID, "bad parameters");
   a.x0 = (const S *)h->x0;
@@ -196,17 +239,17 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
   a.op = op;
   a.n_iters = n_iters;
   a.scalar = S(scalar);
-  auto kern = ilqr_warp_kernel<Model, S, CD>;
-  const size_t smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S>>::Sc, S>(h->desc.T) * kWarpsPerCta;
+  auto kern = ilqr_warp_kernel<Model, S, CD, G>;
+  const size_t smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S, G>>::Sc, S>(h->desc.T) * kGroupsPerCta;
   if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) return fail(h, ILQR_E_CUDA, "kernel does not fit on an SM");
-  long long want = (h->desc.B + kWarpsPerCta - 1) / kWarpsPerCta;
+  long long want = (h->desc.B + kGroupsPerCta - 1) / kGroupsPerCta;
   long long cap = (long long)per_sm * h->num_sms;
   const int grid = (int)(want < cap ? want : cap);
   /* the work buffers of the resident warps (Jacobian columns, FD cost derivatives, line-search candidates) */
-  const long long slots = (long long)grid * kWarpsPerCta;
+  const long long slots = (long long)grid * kGroupsPerCta;
   if (slots > h->slots) {
     CU(h, cudaStreamSynchronize(h->stream));
     void **bufs[] = {&h->slotF, &h->slotC, &h->slotCandX, &h->slotCandU};
@@ -234,8 +277,11 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
 
 template <class Model, typename S>
 int launch_cd(ilqr_handle *h, int op, int n_iters, double scalar) {
-  if (h->desc.cost_deriv == ILQR_COST_ANALYTIC) return launch_t<Model, S, kCostAnalytic>(h, op, n_iters, scalar);
-  return launch_t<Model, S, kCostFD>(h, op, n_iters, scalar);
+  /* two trajectories per warp once the batch can fill the schedulers that way (4 warps per scheduler on 148 SMs) */
+  const bool pack = h->lanes == 16 || (h->lanes == 0 && h->desc.B >= 32768);
+  if (h->desc.cost_deriv == ILQR_COST_ANALYTIC)
+    return pack ? launch_t<Model, S, kCostAnalytic, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostAnalytic, 32>(h, op, n_iters, scalar);
+  return pack ? launch_t<Model, S, kCostFD, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostFD, 32>(h, op, n_iters, scalar);
 }
 template <class Model>
 int launch_s(ilqr_handle *h, int op, int n_iters, double scalar) {
@@ -307,6 +353,7 @@ int ilqr_create(const ilqr_desc *desc, ilqr_handle **out) {
   ilqr_handle *h = new (std::nothrow) ilqr_handle;
   if (!h) return fail(nullptr, ILQR_E_NOMEM, "out of host memory");
   h->desc = *desc;
+  if (const char *e = getenv("ILQR_B200_LANES")) h->lanes = atoi(e) == 16 ? 16 : (atoi(e) == 32 ? 32 : 0);
   h->n = n;
   h->m = m;
   h->ssize = desc->dtype == ILQR_F32 ? 4 : 8;

@@ -140,17 +140,19 @@ struct LaneRegs {
  * stage the small xs / us tiles themselves.  Unaligned tiles fall back to a coalesced lane copy.  (Staging
  * EVERY tile this way with double buffering and prefetch was measured and is slower at this occupancy:
  * profiles/experiments/.) */
-template <int N, int M, typename S>
+template <int N, int M, typename S, int G = 32>
 struct WarpExec {
+  static constexpr int kLanes = G; /* lanes that cooperate on one trajectory: 32, or 16 (two trajectories per warp) */
   LaneRegs<N, M, S> regs;
-  int lane;
-  unsigned bar;         /* shared-window address of the warp's mbarrier */
+  int lane;             /* 0 .. G-1 within the trajectory's lane group */
+  unsigned mask;        /* the lane group's members, for the group barrier */
+  unsigned bar;         /* shared-window address of the group's mbarrier */
   unsigned phase = 0;   /* bit 0: parity to wait for; bit 1: a bulk copy is outstanding */
 
   template <class Fn>
   __device__ __forceinline__ void lanes(Fn fn) {
     fn(lane, regs);
-    __syncwarp();
+    __syncwarp(mask);
   }
   __device__ __forceinline__ static unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
   __device__ __forceinline__ void init_barrier(unsigned long long *b) {
@@ -159,12 +161,12 @@ struct WarpExec {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    __syncwarp(mask);
   }
-  /* global writes of this warp (generic proxy) that a later bulk copy (async proxy) will read */
+  /* global writes of this lane group (generic proxy) that a later bulk copy (async proxy) will read */
   __device__ __forceinline__ void publish() {
     asm volatile("fence.proxy.async;" ::: "memory");
-    __syncwarp();
+    __syncwarp(mask);
   }
   __device__ __forceinline__ void stage_issue(S *dst, const S *src, int count, bool aligned) {
     const unsigned bytes = (unsigned)count * (unsigned)sizeof(S);
@@ -178,7 +180,7 @@ struct WarpExec {
       }
       phase |= 2u;
     } else {
-      for (int e = lane; e < count; e += 32) dst[e] = src[e];
+      for (int e = lane; e < count; e += G) dst[e] = src[e];
     }
   }
   __device__ __forceinline__ void stage_wait() {
@@ -193,17 +195,18 @@ struct WarpExec {
       }
       phase = (phase ^ 1u) & 1u;
     }
-    __syncwarp();
+    __syncwarp(mask);
   }
 };
 #endif
 /* host (tests only): run the phase for lane 0..31 in turn; a staged tile is a plain copy */
-template <int N, int M, typename S>
+template <int N, int M, typename S, int G = 32>
 struct HostExec {
-  LaneRegs<N, M, S> regs[32];
+  static constexpr int kLanes = G;
+  LaneRegs<N, M, S> regs[G];
   template <class Fn>
   void lanes(Fn fn) {
-    for (int l = 0; l < 32; l++) fn(l, regs[l]);
+    for (int l = 0; l < G; l++) fn(l, regs[l]);
   }
   void publish() {}
   void stage_issue(S *dst, const S *src, int count, bool) {
@@ -238,6 +241,7 @@ ILQR_HD S ld_fresh(const S *p) {
 template <class Model, typename S, int CD, class Exec>
 struct Core {
   static constexpr int N = Model::N, M = Model::M, NM = N + M;
+  static constexpr int G = Exec::kLanes; /* lanes cooperating on this trajectory */
   using Sc = Scratch<N, M, S, CD>;
   using Lane = LaneRegs<N, M, S>;
   static constexpr int NA = Sc::NA, NCF = Sc::NCF;
@@ -398,7 +402,7 @@ struct Core {
   ILQR_HD void derivative_sweep() {
     const int T = P.T;
     const int n_dyn = T * NM;
-    for (int base = 0; base < n_dyn; base += 32) {
+    for (int base = 0; base < n_dyn; base += G) {
       ex.lanes([&](int lane, Lane &) {
         const int task = base + lane;
         if (task >= n_dyn) return;
@@ -420,7 +424,7 @@ struct Core {
     }
     if constexpr (CD == kCostFD) {
       const int n_c = T * kStencilStep;
-      for (int base = 0; base < n_c; base += 32) {
+      for (int base = 0; base < n_c; base += G) {
         ex.lanes([&](int lane, Lane &) {
           const int task = base + lane;
           if (task >= n_c) return;
@@ -441,13 +445,13 @@ struct Core {
   ILQR_HD void phase_terminal() {
     ex.lanes([&](int lane, Lane &) {
       if (CD == kCostFD) {
-        for (int o = lane; o < kStencilTerm; o += 32) cost_stencil(o, true, sc.x, sc.u, sc.Cf);
+        for (int o = lane; o < kStencilTerm; o += G) cost_stencil(o, true, sc.x, sc.u, sc.Cf);
       } else if (lane == 0) {
         analytic_cost(sc.x, sc.u, true, sc.Cf);
       }
     });
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * NA; e += 32) {
+      for (int e = lane; e < N * NA; e += G) {
         const int r = e / NA, b = e % NA;
         sc.Va[e] = (b < N) ? sc.Cf[ix_cxx(r, b < N ? b : 0)] : sc.Cf[r];
       }
@@ -466,7 +470,7 @@ struct Core {
     const S *ut = sc.us + tt * M;
     /* W = F^T [Vxx' | Vx']  (:359-363): column n gives Qx = cx + fx^T Vx', Qu = cu + fu^T Vx' */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < NM * NA; e += 32) {
+      for (int e = lane; e < NM * NA; e += G) {
         const int c = e / NA, b = e % NA;
         Acc<S> acc;
 #pragma unroll
@@ -481,7 +485,7 @@ struct Core {
     });
     /* Q[c][d] = C[c][d] + sum_r W[c][r] F[d][r]: Qxx, Qux, Quu (:361-363) and the regularised QuuF (:367) */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < NM * NM; e += 32) {
+      for (int e = lane; e < NM * NM; e += G) {
         const int c = e / NM, d = e % NM;
         Acc<S> acc;
 #pragma unroll
@@ -559,7 +563,7 @@ struct Core {
     if (sc.qp.result < 1) return false;
     /* [Vxx | Vx] before symmetrisation (:391-392): column b < n is Vxx[:, b], column n is Vx */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * NA; e += 32) {
+      for (int e = lane; e < N * NA; e += G) {
         const int a = e / NA, b = e % NA;
         S ktq[M]; /* row a of K^T Quu */
 #pragma unroll
@@ -582,7 +586,7 @@ struct Core {
     /* symmetrise (:393) and roll the value function; the closed-form cost derivatives of the next
      * timestep (tt - 1) are prepared on the last lane */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * NA; e += 32) {
+      for (int e = lane; e < N * NA; e += G) {
         const int a = e / NA, b = e % NA;
         const int bt = (b < N) ? b : a; /* column n (Vx) is copied: 0.5 * (v + v) == v exactly */
         const int at = (b < N) ? a : N;
@@ -590,7 +594,7 @@ struct Core {
         const S v2 = (b < N) ? sc.Vt[bt * NA + at] : v1;
         sc.Va[e] = S(0.5) * (v1 + v2);
       }
-      if (CD == kCostAnalytic && lane == 31 && tt > 0) analytic_cost(sc.xs + (tt - 1) * N, sc.us + (tt - 1) * M, false, sc.Cf);
+      if (CD == kCostAnalytic && lane == G - 1 && tt > 0) analytic_cost(sc.xs + (tt - 1) * N, sc.us + (tt - 1) * M, false, sc.Cf);
     });
     return true;
   }
@@ -617,10 +621,10 @@ struct Core {
       const int cnt = (T - t0 < kTileB) ? T - t0 : kTileB;
       ex.stage_issue(sc.Ft, sl.F + (size_t)t0 * NM * N, cnt * NM * N, P.bulk_f != 0);
       ex.lanes([&](int lane, Lane &) {
-        for (int e = lane; e < cnt * N; e += 32) sc.xs[e] = tr.xs[t0 * N + e];
-        for (int e = lane; e < cnt * M; e += 32) sc.us[e] = tr.us[t0 * M + e];
+        for (int e = lane; e < cnt * N; e += G) sc.xs[e] = tr.xs[t0 * N + e];
+        for (int e = lane; e < cnt * M; e += G) sc.us[e] = tr.us[t0 * M + e];
         if constexpr (CD == kCostFD) {
-          for (int e = lane; e < cnt * NCF; e += 32) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NCF + e);
+          for (int e = lane; e < cnt * NCF; e += G) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NCF + e);
         }
       });
       ex.stage_wait();
@@ -640,15 +644,15 @@ struct Core {
       }
       /* flush the tile's k / K and the gradient-norm terms of its timesteps (:405-412), one per lane */
       ex.lanes([&](int lane, Lane &) {
-        for (int e = lane + first_done * M * N; e < cnt * M * N; e += 32) tr.K[t0 * M * N + e] = sc.K[e];
-        for (int e = lane + first_done * M; e < cnt * M; e += 32) tr.k[t0 * M + e] = sc.k[e];
-        for (int e = lane + first_done; e < cnt; e += 32) sl.gterm[t0 + e] = gn_term(sc.k + e * M, sc.us + e * M);
+        for (int e = lane + first_done * M * N; e < cnt * M * N; e += G) tr.K[t0 * M * N + e] = sc.K[e];
+        for (int e = lane + first_done * M; e < cnt * M; e += G) tr.k[t0 * M + e] = sc.k[e];
+        for (int e = lane + first_done; e < cnt; e += G) sl.gterm[t0 + e] = gn_term(sc.k + e * M, sc.us + e * M);
       });
     }
     if (diverged_at >= 0) return diverged_at;
     /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * NA; e += 32) {
+      for (int e = lane; e < N * NA; e += G) {
         const int r = e / NA, b = e % NA;
         if (b < N) tr.Vxx0[r * N + b] = sc.Va[e];
         else tr.Vx0[r] = sc.Va[e];
@@ -714,11 +718,11 @@ struct Core {
 
   ILQR_HD void load_forward_tile(int t0, int cnt, int mode) {
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < cnt * N; e += 32) sc.xs[e] = tr.xs[t0 * N + e];
-      for (int e = lane; e < cnt * M; e += 32) sc.us[e] = tr.us[t0 * M + e];
+      for (int e = lane; e < cnt * N; e += G) sc.xs[e] = tr.xs[t0 * N + e];
+      for (int e = lane; e < cnt * M; e += G) sc.us[e] = tr.us[t0 * M + e];
       if (mode != kRollOpen) {
-        for (int e = lane; e < cnt * M * N; e += 32) sc.K[e] = tr.K[t0 * M * N + e];
-        for (int e = lane; e < cnt * M; e += 32) sc.k[e] = tr.k[t0 * M + e];
+        for (int e = lane; e < cnt * M * N; e += G) sc.K[e] = tr.K[t0 * M * N + e];
+        for (int e = lane; e < cnt * M; e += G) sc.k[e] = tr.k[t0 * M + e];
       }
     });
   }
@@ -770,8 +774,8 @@ struct Core {
     ex.lanes([&](int lane, Lane &) {
       const S *cx = sl.cand_x + (size_t)a * T * N;
       const S *cu = sl.cand_u + (size_t)a * T * M;
-      for (int e = lane; e < T * N; e += 32) tr.xs[N + e] = ld_fresh(cx + e);
-      for (int e = lane; e < T * M; e += 32) tr.us[e] = ld_fresh(cu + e);
+      for (int e = lane; e < T * N; e += G) tr.xs[N + e] = ld_fresh(cx + e);
+      for (int e = lane; e < T * M; e += G) tr.us[e] = ld_fresh(cu + e);
     });
   }
 
@@ -890,122 +894,137 @@ struct Core {
     store_state();
   }
 
-  /* the loop body of iLQR::generate_trajectory() (:103-288), up to n_iters trips */
-  ILQR_HD void op_iterate(int n_iters) {
+  /* The loop of iLQR::generate_trajectory() (:103-288), up to n_iters trips, as three calls so that a warp
+   * carrying two trajectories can advance both one trip at a time in lockstep:
+   *   iterate_begin(n);  while (iterate_trip()) {}  iterate_end();                                      */
+  int trips_left = 0;
+  bool have_derivs = false; /* the lane group's F / C buffers hold this trajectory's current derivatives */
+
+  ILQR_HD void iterate_begin(int n_iters) {
     load_state();
-    int done_here = 0;
-    bool have_derivs = false; /* the warp's F / C buffers hold this trajectory's current derivatives */
-    while (sc.st.iter < P.max_iter && done_here < n_iters && sc.st.status == kRunning) {
-      done_here++;
-      /* :115-120 */
-      if (sc.st.flg_change || !have_derivs) {
-        derivative_sweep();
-        have_derivs = true;
-      }
-      ex.lanes([&](int lane, Lane &) {
-        if (lane != 0) return;
-        sc.st.trips++;
-        if (sc.st.flg_change) {
-          sc.st.flg_change = 0;
-          sc.st.n_deriv++;
-        }
-        sc.flag = 0;
-      });
-      /* :136-150 */
-      bool back_done = false;
-      while (!back_done) {
-        const int diverge = backward_pass(sc.st.lam);
-        ex.lanes([&](int lane, Lane &) {
-          if (lane != 0) return;
-          TrajState<S> &s = sc.st;
-          s.diverge = diverge;
-          sc.flag = 0;
-          if (diverge != 0) {
-            s.dlam = fmax_(s.dlam * P.lambda_factor, P.lambda_factor);
-            s.lam = fmax_(s.lam * s.dlam, P.lambda_min);
-            if (s.lam > P.lambda_max) sc.flag = 1;
-          }
-        });
-        if (diverge != 0) {
-          if (sc.flag) break;
-          continue;
-        }
-        back_done = true;
-      }
-      if (back_done) gradient_norm_from_terms();
-      else gradient_norm_only();
-      /* :153-159 */
-      ex.lanes([&](int lane, Lane &) {
-        if (lane != 0) return;
-        sc.flag = 0;
-        if (sc.st.gnorm < P.tol_grad && sc.st.lam < P.grad_lambda_gate) {
-          sc.st.status = kExitGrad;
-          sc.flag = 2;
-        }
-      });
-      if (sc.flag == 2) break; /* gradient exit: `break` before iter++ */
-      if (back_done) rollout_candidates();
-      /* the acceptance test :199-213 in the reference's serial order */
-      ex.lanes([&](int lane, Lane &) {
-        if (lane != 0) return;
-        TrajState<S> &s = sc.st;
-        sc.flag = 0;
-        s.alpha_index = -1;
-        S alpha = 0;
-        if (back_done) {
-          for (int a = 0; a < P.n_alpha; a++) {
-            alpha = P.alpha[a];
-            s.new_cost = sc.newcost[a];
-            s.n_rollouts++;
-            s.dcost = s.cost - s.new_cost;
-            s.expected = -alpha * (s.dV0 + alpha * s.dV1);
-            S z;
-            if (s.expected > 0) z = s.dcost / s.expected;
-            else z = S((S(0) < s.dcost) - (s.dcost < S(0))); /* sgn, include/common.h:43-44 */
-            if (z > P.z_min) {
-              s.alpha_index = a;
-              sc.flag = 1;
-              break;
-            }
-          }
-          if (!sc.flag) alpha = 0;
-        }
-        s.alpha = alpha;
-      });
-      const bool fwd_done = sc.flag == 1;
-      if (fwd_done) commit_candidate(sc.st.alpha_index);
-      ex.lanes([&](int lane, Lane &) {
-        if (lane != 0) return;
-        TrajState<S> &s = sc.st;
-        sc.flag = 0;
-        if (fwd_done) { /* :242-263 */
-          s.dlam = fmin_(s.dlam / P.lambda_factor, 1 / P.lambda_factor);
-          s.lam = s.lam * s.dlam * S(s.lam > P.lambda_min);
-          s.cost = s.new_cost;
-          s.flg_change = 1;
-          s.n_accept++;
-          if (s.dcost < P.tol_fun) {
-            s.status = kExitTolFun;
-            sc.flag = 1;
-          }
-        } else { /* :264-282 */
-          s.dlam = fmax_(s.dlam * P.lambda_factor, P.lambda_factor);
-          s.lam = fmax_(s.lam * s.dlam, P.lambda_min);
-          s.n_reject++;
-          if (s.lam > P.lambda_max) {
-            s.status = kExitLambdaMax;
-            sc.flag = 1;
-          }
-        }
-        if (!sc.flag) s.iter++;
-      });
-      if (sc.flag) break;
-    }
+    trips_left = n_iters;
+    have_derivs = false;
+  }
+  ILQR_HD void iterate_end() {
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
       if (sc.st.status == kRunning && sc.st.iter >= P.max_iter) sc.st.status = kExitMaxIter;
     });
     store_state();
+  }
+  /* one trip of the loop body; returns whether another one follows */
+  ILQR_HD bool iterate_trip() {
+    if (!(sc.st.iter < P.max_iter && trips_left > 0 && sc.st.status == kRunning)) return false;
+    trips_left--;
+    /* :115-120 */
+    if (sc.st.flg_change || !have_derivs) {
+      derivative_sweep();
+      have_derivs = true;
+    }
+    ex.lanes([&](int lane, Lane &) {
+      if (lane != 0) return;
+      sc.st.trips++;
+      if (sc.st.flg_change) {
+        sc.st.flg_change = 0;
+        sc.st.n_deriv++;
+      }
+      sc.flag = 0;
+    });
+    /* :136-150 */
+    bool back_done = false;
+    while (!back_done) {
+      const int diverge = backward_pass(sc.st.lam);
+      ex.lanes([&](int lane, Lane &) {
+        if (lane != 0) return;
+        TrajState<S> &s = sc.st;
+        s.diverge = diverge;
+        sc.flag = 0;
+        if (diverge != 0) {
+          s.dlam = fmax_(s.dlam * P.lambda_factor, P.lambda_factor);
+          s.lam = fmax_(s.lam * s.dlam, P.lambda_min);
+          if (s.lam > P.lambda_max) sc.flag = 1;
+        }
+      });
+      if (diverge != 0) {
+        if (sc.flag) break;
+        continue;
+      }
+      back_done = true;
+    }
+    if (back_done) gradient_norm_from_terms();
+    else gradient_norm_only();
+    /* :153-159 */
+    ex.lanes([&](int lane, Lane &) {
+      if (lane != 0) return;
+      sc.flag = 0;
+      if (sc.st.gnorm < P.tol_grad && sc.st.lam < P.grad_lambda_gate) {
+        sc.st.status = kExitGrad;
+        sc.flag = 2;
+      }
+    });
+    if (sc.flag == 2) return false; /* gradient exit: `break` before iter++ */
+    if (back_done) rollout_candidates();
+    /* the acceptance test :199-213 in the reference's serial order */
+    ex.lanes([&](int lane, Lane &) {
+      if (lane != 0) return;
+      TrajState<S> &s = sc.st;
+      sc.flag = 0;
+      s.alpha_index = -1;
+      S alpha = 0;
+      if (back_done) {
+        for (int a = 0; a < P.n_alpha; a++) {
+          alpha = P.alpha[a];
+          s.new_cost = sc.newcost[a];
+          s.n_rollouts++;
+          s.dcost = s.cost - s.new_cost;
+          s.expected = -alpha * (s.dV0 + alpha * s.dV1);
+          S z;
+          if (s.expected > 0) z = s.dcost / s.expected;
+          else z = S((S(0) < s.dcost) - (s.dcost < S(0))); /* sgn, include/common.h:43-44 */
+          if (z > P.z_min) {
+            s.alpha_index = a;
+            sc.flag = 1;
+            break;
+          }
+        }
+        if (!sc.flag) alpha = 0;
+      }
+      s.alpha = alpha;
+    });
+    const bool fwd_done = sc.flag == 1;
+    if (fwd_done) commit_candidate(sc.st.alpha_index);
+    ex.lanes([&](int lane, Lane &) {
+      if (lane != 0) return;
+      TrajState<S> &s = sc.st;
+      sc.flag = 0;
+      if (fwd_done) { /* :242-263 */
+        s.dlam = fmin_(s.dlam / P.lambda_factor, 1 / P.lambda_factor);
+        s.lam = s.lam * s.dlam * S(s.lam > P.lambda_min);
+        s.cost = s.new_cost;
+        s.flg_change = 1;
+        s.n_accept++;
+        if (s.dcost < P.tol_fun) {
+          s.status = kExitTolFun;
+          sc.flag = 1;
+        }
+      } else { /* :264-282 */
+        s.dlam = fmax_(s.dlam * P.lambda_factor, P.lambda_factor);
+        s.lam = fmax_(s.lam * s.dlam, P.lambda_min);
+        s.n_reject++;
+        if (s.lam > P.lambda_max) {
+          s.status = kExitLambdaMax;
+          sc.flag = 1;
+        }
+      }
+      if (!sc.flag) s.iter++;
+    });
+    return sc.flag == 0;
+  }
+  ILQR_HD void op_iterate(int n_iters) {
+    iterate_begin(n_iters);
+    while (iterate_trip()) {
+    }
+    iterate_end();
   }
 
   ILQR_HD static S fmax_(S a, S b) { return a < b ? b : a; } /* std::max(a, b) */

@@ -47,10 +47,9 @@ struct Acrobot {
     const S I1 = 1, I2 = 1, l1 = 1, l2 = 1, m1 = 1, m2 = 1, g = S(9.81);
     const S lc1 = S(0.5) * l1, lc2 = S(0.5) * l2;
     const S q0 = x[0], q1 = x[1], qd0 = x[2], qd1 = x[3];
-    S c2, s2, s1, s1p2, unused;
-    sincos_det(q1, &s2, &c2);
-    sincos_det(q0, &s1, &unused);
-    sincos_det(q0 + q1, &s1p2, &unused);
+    S sn[3], cs[3];
+    sincos_det3(q1, q0, q0 + q1, sn, cs);
+    const S c2 = cs[0], s2 = sn[0], s1 = sn[1], s1p2 = sn[2];
     const S H00 = I1 + I2 + m2 * l1 * l1 + 2 * m2 * l1 * lc2 * c2;
     const S H01 = I2 + m2 * l1 * lc2 * c2;
     const S H10 = I2 + m2 * l1 * lc2 * c2;

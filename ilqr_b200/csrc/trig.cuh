@@ -50,13 +50,14 @@ static const double kTrigHost[16] = ILQR_TRIG_TABLE;
 #define ILQR_HD_TRIG ILQR_HD
 #endif
 
-ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
-#if defined(ILQR_TRIG_LIBM) && !defined(__CUDACC__)
-  /* tests/emu only: the platform libm, to compare the kernel source bit for bit with the oracle */
-  *sn = ::sin(x);
-  *cs = ::cos(x);
-  return;
-#endif
+/* |x| small enough for the two-step Cody-Waite reduction (fdlibm's "medium" range is 2^19 * pi/2) */
+ILQR_HD bool sincos_in_range(double x) { return ::fabs(x) < 8.0e5; } /* false for NaN */
+
+/* The branch-free core: exact for sincos_in_range(x), meaningless (but harmless) otherwise.  Callers that
+ * need several sincos of independent arguments call this back to back and test the ranges once afterwards,
+ * so the evaluations sit in one basic block and the instruction scheduler interleaves their dependency
+ * chains (a branch per call would serialise them). */
+ILQR_HD void sincos_core(double x, double *sn, double *cs) {
 #if defined(__CUDA_ARCH__)
   const double *tab = kTrigDev;
 #else
@@ -65,10 +66,6 @@ ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
   const double invpio2 = tab[0], pio2_1 = tab[1], pio2_2 = tab[2], pio2_2t = tab[3];
   const double S1 = tab[4], S2 = tab[5], S3 = tab[6], S4 = tab[7], S5 = tab[8], S6 = tab[9];
   const double C1 = tab[10], C2 = tab[11], C3 = tab[12], C4 = tab[13], C5 = tab[14], C6 = tab[15];
-  if (!(::fabs(x) < 8.0e5)) { /* also catches NaN */
-    ::sincos(x, sn, cs);
-    return;
-  }
   /* x = n * pi/2 + (y0 + y1), |y0| <= pi/4 (+ rounding), 118-bit pi/2 */
   const double fn = ::rint(x * invpio2);
   const int n = (int)fn;
@@ -94,7 +91,44 @@ ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
   *cs = ((n + 1) & 2) ? -b : b;
 }
 
+ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
+#if defined(ILQR_TRIG_LIBM) && !defined(__CUDACC__)
+  /* tests/emu only: the platform libm, to compare the kernel source bit for bit with the oracle */
+  *sn = ::sin(x);
+  *cs = ::cos(x);
+  return;
+#endif
+  if (!sincos_in_range(x)) {
+    ::sincos(x, sn, cs);
+    return;
+  }
+  sincos_core(x, sn, cs);
+}
+
+/* three at once (the acrobot's arguments), interleaved; same results as three sincos_det calls */
+ILQR_HD void sincos_det3(double x0, double x1, double x2, double *sn, double *cs) {
+#if defined(ILQR_TRIG_LIBM) && !defined(__CUDACC__)
+  sincos_det(x0, sn + 0, cs + 0);
+  sincos_det(x1, sn + 1, cs + 1);
+  sincos_det(x2, sn + 2, cs + 2);
+  return;
+#endif
+  sincos_core(x0, sn + 0, cs + 0);
+  sincos_core(x1, sn + 1, cs + 1);
+  sincos_core(x2, sn + 2, cs + 2);
+  if (!(sincos_in_range(x0) && sincos_in_range(x1) && sincos_in_range(x2))) {
+    sincos_det(x0, sn + 0, cs + 0);
+    sincos_det(x1, sn + 1, cs + 1);
+    sincos_det(x2, sn + 2, cs + 2);
+  }
+}
+
 ILQR_HD void sincos_det(float x, float *sn, float *cs) { ::sincosf(x, sn, cs); }
+ILQR_HD void sincos_det3(float x0, float x1, float x2, float *sn, float *cs) {
+  ::sincosf(x0, sn + 0, cs + 0);
+  ::sincosf(x1, sn + 1, cs + 1);
+  ::sincosf(x2, sn + 2, cs + 2);
+}
 
 }  // namespace ilqr
 #endif

@@ -31,13 +31,13 @@ struct EmuBase {
   int n = 0, m = 0;
 };
 
-template <class Model, typename S, int CD>
+template <class Model, typename S, int CD, int G>
 struct Emu : EmuBase {
   static constexpr int N = Model::N, M = Model::M;
   ilqr_desc desc;
   SolveParams<S> P;
-  typename Core<Model, S, CD, HostExec<N, M, S>>::Sc sc;
-  HostExec<N, M, S> ex;
+  typename Core<Model, S, CD, HostExec<N, M, S, G>>::Sc sc;
+  HostExec<N, M, S, G> ex;
   std::vector<S> x0, xs, us, K, k, Vx0, Vxx0, gterm, bufF, bufC, candX, candU;
   TrajState<S> st;
   int T = 0;
@@ -69,7 +69,7 @@ struct Emu : EmuBase {
     w.gterm = gterm.data();
     return w;
   }
-  Core<Model, S, CD, HostExec<N, M, S>> core() { return Core<Model, S, CD, HostExec<N, M, S>>(P, sc, ex, ptrs(), slot()); }
+  Core<Model, S, CD, HostExec<N, M, S, G>> core() { return Core<Model, S, CD, HostExec<N, M, S, G>>(P, sc, ex, ptrs(), slot()); }
 
   double init(const double *x0_, const double *u0_, int T_) override {
     T = T_;
@@ -152,10 +152,16 @@ struct Emu : EmuBase {
   }
 };
 
+int g_lanes = 32; /* lanes per trajectory of the next emu_new: 32 (one trajectory per warp) or 16 (two per warp) */
+
 template <class Model, typename S>
 EmuBase *make_cd(const ilqr_desc &d) {
-  if (d.cost_deriv == ILQR_COST_ANALYTIC) return new Emu<Model, S, kCostAnalytic>(d);
-  return new Emu<Model, S, kCostFD>(d);
+  if (g_lanes == 16) {
+    if (d.cost_deriv == ILQR_COST_ANALYTIC) return new Emu<Model, S, kCostAnalytic, 16>(d);
+    return new Emu<Model, S, kCostFD, 16>(d);
+  }
+  if (d.cost_deriv == ILQR_COST_ANALYTIC) return new Emu<Model, S, kCostAnalytic, 32>(d);
+  return new Emu<Model, S, kCostFD, 32>(d);
 }
 template <class Model>
 EmuBase *make_dtype(const ilqr_desc &d) {
@@ -196,6 +202,8 @@ int run_qp(const ilqr_params &p, int generic, const double *Q, const double *c, 
 }  // namespace
 
 extern "C" {
+
+void emu_set_lanes(int lanes) { g_lanes = lanes == 16 ? 16 : 32; }
 
 void *emu_new(const ilqr_desc *d) {
   if (d->model_id == ILQR_MODEL_ACROBOT) return make_dtype<Acrobot>(*d);

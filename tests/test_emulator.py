@@ -23,8 +23,8 @@ SCAL = ("lam", "dlam", "gnorm", "dcost", "expected", "alpha", "new_cost")
 CNT = ("iter", "loop_trips", "status", "alpha_index", "accepts", "rejects", "rollouts", "backwards", "derivs", "diverge")
 
 
-def lockstep(model, x0, u0, dt, libm, max_trips=101, **kw):
-    o, e = O.OracleSolver(model, dt, **kw), E.EmuSolver(model, dt, libm=libm, **kw)
+def lockstep(model, x0, u0, dt, libm, max_trips=101, lanes=32, **kw):
+    o, e = O.OracleSolver(model, dt, **kw), E.EmuSolver(model, dt, libm=libm, lanes=lanes, **kw)
     assert o.init(x0, u0) == e.init(x0, u0)
     assert np.array_equal(o.get("xs"), e.get("xs"))
     assert o.backward_once(1.0) == e.backward_once(1.0)
@@ -68,6 +68,18 @@ def test_double_integrator_kernel_source_equals_oracle_bit_for_bit(golden_solver
     g = golden_solver
     lockstep(abi.MODEL_DOUBLE_INTEGRATOR, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), libm,
              goal=list(g[case + "/goal"]), cost_deriv=cd)
+
+
+@pytest.mark.parametrize("case,model,cd,kw", [
+    ("acrobot_T200_b1", abi.MODEL_ACROBOT, abi.COST_FD, {}), ("acrobot_T200_b4", abi.MODEL_ACROBOT, abi.COST_ANALYTIC, {}),
+    ("acrobot_lim15_T200_b0", abi.MODEL_ACROBOT, abi.COST_FD, dict(u_min=[-1.5], u_max=[1.5])),
+    ("integrator_rand_T60_b1", abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, None)])
+def test_sixteen_lane_decomposition_equals_oracle_bit_for_bit(golden_solver, case, model, cd, kw):
+    """the lane decomposition used when a warp carries two trajectories (16 lanes each)"""
+    g = golden_solver
+    if kw is None:
+        kw = dict(goal=list(g[case + "/goal"]))
+    lockstep(model, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), True, lanes=16, cost_deriv=cd, **kw)
 
 
 def test_warm_start_kernel_source_equals_oracle():
