@@ -9,9 +9,9 @@
  * the iLQR iterates depend on them.  `R^-1 R^-T` is formed the way the reference forms it: two
  * dense inverses by partially pivoted LU (Eigen/src/LU/InverseImpl.h:23-28) and a product.
  *
- * One lane of the warp runs a problem; Q, c and the work arrays live in the warp's shared-memory
- * scratch, so the dynamic indexing of the free-set gathers costs nothing.  m == 1 (acrobot) has a
- * scalar fast path with the same arithmetic.
+ * m > 1: one lane of the warp runs a problem; Q, c and the work arrays live in the warp's
+ * shared-memory scratch, so the dynamic indexing of the free-set gathers costs nothing.
+ * m == 1 (acrobot): a scalar version with the same arithmetic, entirely in registers.
  */
 #ifndef ILQR_BOXQP_CUH_
 #define ILQR_BOXQP_CUH_
@@ -279,21 +279,72 @@ ILQR_HD void box_qp_generic(const QPParams<S> &p, QPWork<M, S> &w) {
   if (w.result >= 1 && any_free) rinv_rtinv(w, w.r_dim, w.Hinv);
 }
 
-/* m == 1: the same arithmetic on scalars held in registers.  Three values the general code
- * recomputes are reused here because they are bit-identical by construction: 1/R is formed once
- * for R^-1 and R^-T (the same division), sqrt(grad^2) is |grad| (exact in IEEE-754 away from
- * over/underflow, where both sides of the `< minGrad` test agree anyway), and the R^-1 R^-T the
- * gain computation needs (ilqr_core.cpp:379) is the one of the last Newton step because R is only
- * ever factorised once when there is a single variable. */
+/* m == 1: the same arithmetic on scalars held in registers; nothing touches memory, so every lane
+ * of the warp can run it redundantly (ilqr_core.cuh, backward_step).  Values the general code
+ * recomputes are formed once because they are bit-identical by construction: R is only ever
+ * factorised at iteration 0 when there is a single variable (the flag difference of :80 is 0 - 0
+ * afterwards: a clamped variable leaves the loop at once), 1/R is the same division for R^-1 and
+ * R^-T, sqrt(grad^2) is |grad| (exact in IEEE-754 away from over/underflow, where both sides of
+ * the `< minGrad` test agree anyway), and the R^-1 R^-T of the gain computation
+ * (ilqr_core.cpp:379) is the one of the Newton steps.  sqrt(Q) -> 1/R -> 1/R^2 is the longest
+ * dependency chain of a backward timestep, so it is issued first, unconditionally (the values
+ * are only READ where the reference computes them), and overlaps the clamp / gradient tests.
+ *
+ * The Armijo test of quadclamp_line_search (:161), (v - old_v) / (step * slope) < armijo, costs a
+ * double-precision division per trial.  With den = step * slope < 0 it is decided exactly by
+ * comparing num with armijo * den whenever the two differ by more than a few dozen ulp (then the
+ * correctly rounded quotient lies on the same side of `armijo` as the real one); only in the
+ * remaining sliver, or when den is not a normal finite number, is the division carried out. */
 template <typename S>
-ILQR_HD void box_qp_scalar(const QPParams<S> &p, QPWork<1, S> &w) {
-  const S Q = w.Q[0], c = w.c[0], lo = w.lo[0], hi = w.hi[0];
-  S x = clampd(w.x0[0], lo, hi);
-  S val = (x * Q) * x + x * c;
+struct QPScalar {
+  S x, R, Hinv;
+  int v_free, result;
+};
+
+#if defined(ILQR_QP_STATS) && !defined(__CUDA_ARCH__)
+#include <stdio.h>
+#include <stdlib.h>
+static long g_qp_calls, g_qp_fast[8], g_qp_slow_arm[3], g_qp_bt, g_qp_loop_iters;
+static void qp_stats_print() {
+  fprintf(stderr, "qp calls %ld fast results [2]=%ld [4]=%ld [5]=%ld [6]=%ld; slow: armijo-fail %ld ambiguous %ld third-iteration %ld; backtracks %ld loop iters %ld\n",
+          g_qp_calls, g_qp_fast[2], g_qp_fast[4], g_qp_fast[5], g_qp_fast[6], g_qp_slow_arm[1], g_qp_slow_arm[2], g_qp_slow_arm[0], g_qp_bt, g_qp_loop_iters);
+}
+static void qp_stats(int result, int arm) {
+  if (g_qp_calls++ == 0) atexit(qp_stats_print);
+  if (result >= 0) g_qp_fast[result & 7]++;
+  else g_qp_slow_arm[arm < 0 ? 2 : arm]++;
+}
+#endif
+
+/* The Armijo test with den < 0: 1 = fails (backtrack), 0 = passes, -1 = too close to call without the division */
+template <typename S>
+ILQR_HD int armijo_quick(S num, S den, S armijo) {
+  const S p = armijo * den;
+  const S ap = t_abs(p);
+  const S diff = num - p;
+  const S tol = S(64) * (sizeof(S) == 8 ? S(2.220446049250313e-16) : S(1.1920929e-07));
+  const bool definite = ap > S(1e-30) && ap < S(1e30) && t_abs(diff) > tol * ap;
+  return definite ? (num > p ? 1 : 0) : -1; /* den < 0 flips the inequality */
+}
+template <typename S>
+ILQR_HD bool armijo_fails(S num, S den, S armijo) {
+  const int q = armijo_quick(num, den, armijo);
+  return q >= 0 ? q != 0 : num / den < armijo;
+}
+
+template <typename S>
+ILQR_HD bool qp_is_clamped(const QPParams<S> &p, S x, S grad, S lo, S hi) { /* :62-71 */
+  return (t_abs(x - lo) < p.clamp_tol && grad > 0) || (t_abs(x - hi) < p.clamp_tol && grad < 0);
+}
+
+/* the loop of boxQP as written, from the start (every exit the reference has) */
+template <typename S>
+ILQR_HD QPScalar<S> box_qp_scalar_loop(const QPParams<S> &p, S Q, S c, S x0, S lo, S hi, S R, S Hinv) {
+  S x = clampd(x0, lo, hi);
+  S val = (x * Q) * x + x * c; /* :36, no 1/2 */
   S oldvalue = 0;
-  S R = 0, Hinv = 0;
-  bool have_hinv = false;
   int result = 0, vfree = 1;
+  bool factorised = false;
   for (int iter = 0; iter <= p.max_iter; iter++) {
     if (iter > 0 && (oldvalue - val) < p.min_rel_improve * t_abs(oldvalue)) {
       result = 4;
@@ -302,23 +353,17 @@ ILQR_HD void box_qp_scalar(const QPParams<S> &p, QPWork<1, S> &w) {
     const S grad = Q * x + c;
     oldvalue = val;
     vfree = 1;
-    if ((t_abs(x - lo) < p.clamp_tol && grad > 0) || (t_abs(x - hi) < p.clamp_tol && grad < 0)) {
+    if (qp_is_clamped(p, x, grad, lo, hi)) {
       vfree = 0;
       result = 6;
       break;
     }
-    /* the flag difference of :80 is 0 - 0 here (a clamped variable has just left the loop): factorise at iter 0 only */
-    if (iter == 0) R = (Q <= 0) ? Q : t_sqrt(Q);
+    factorised = true; /* :80-90 */
     if (t_abs(grad) < p.min_grad) { /* sqrt(grad * grad) */
       result = 5;
       break;
     }
     const S grad_clamped = Q * (x * S(0)) + c;
-    if (!have_hinv) {
-      const S Ri = S(1) / R;
-      Hinv = Ri * Ri;
-      have_hinv = true;
-    }
     const S search = (-Hinv) * grad_clamped - x;
     /* quadclamp_line_search */
     const S slope = search * grad;
@@ -331,7 +376,10 @@ ILQR_HD void box_qp_scalar(const QPParams<S> &p, QPWork<1, S> &w) {
     S v = ((S(0.5) * xc) * Q) * xc + xc * c;
     const S old_v = ((S(0.5) * x) * Q) * x + x * c;
     bool failed = false;
-    while ((v - old_v) / (step * slope) < p.armijo) {
+    while (armijo_fails(v - old_v, step * slope, p.armijo)) {
+#if defined(ILQR_QP_STATS) && !defined(__CUDA_ARCH__)
+      g_qp_bt++;
+#endif
       step *= p.step_dec;
       xc = clampd(x + step * search, lo, hi);
       v = ((S(0.5) * xc) * Q) * xc + xc * c;
@@ -347,24 +395,100 @@ ILQR_HD void box_qp_scalar(const QPParams<S> &p, QPWork<1, S> &w) {
     x = xc;
     val = v;
   }
-  w.x[0] = x;
-  w.v_free[0] = vfree;
-  w.R[0] = R;
-  w.r_dim = 1;
-  w.result = result;
-  if (result >= 1 && vfree) {
-    if (!have_hinv) {
-      const S Ri = S(1) / R;
-      Hinv = Ri * Ri;
-    }
-    w.Hinv[0] = Hinv;
-  }
+  QPScalar<S> r;
+  r.x = x;
+  r.R = factorised ? R : S(0);
+  r.Hinv = Hinv;
+  r.v_free = vfree;
+  r.result = result;
+  return r;
 }
 
+/* Nearly every call ends in its first or second Newton iteration (clamped at once; or one step, then
+ * "gradient small" / "all clamped" / "no improvement").  Those two iterations are written out as straight-line
+ * code — every quantity either of them may need, then the reference's tests in the reference's order on the
+ * finished values — so that the independent dependency chains (sqrt -> 1/R -> 1/R^2; x, value, gradient and
+ * the clamp tests; the trial point with its value; the second gradient) overlap in the instruction stream
+ * instead of queueing behind the loop's branches.  One call in ten has to back-track in the first line search
+ * (a step cut short by a bound, measured on the BASELINE batch): that loop is the reference's, then the
+ * second iteration's tests are redone on its result.  Anything else (a third iteration) runs the reference's
+ * loop from the start.  Same operations on the same operands whichever way. */
+template <typename S>
+ILQR_HD QPScalar<S> box_qp_scalar(const QPParams<S> &p, S Q, S c, S x0, S lo, S hi) {
+  /* iteration 0 */
+  const S x = clampd(x0, lo, hi);
+  const S grad0 = Q * x + c;
+  const S val0 = (x * Q) * x + x * c; /* :36, no 1/2 */
+  const bool clamped0 = qp_is_clamped(p, x, grad0, lo, hi);
+  const bool small0 = t_abs(grad0) < p.min_grad;
+  const S gc0 = Q * (x * S(0)) + c;
+  const S R = (Q <= 0) ? Q : t_sqrt(Q); /* Eigen LLT leaves a non-positive pivot as it is */
+  const S Ri = S(1) / R;
+  const S Hinv = Ri * Ri;
+  const S search = (-Hinv) * gc0 - x;
+  const S slope = search * grad0;
+  const bool ascent = slope >= 0;
+  S xc = clampd(x + search, lo, hi); /* step = 1 */
+  S v = ((S(0.5) * xc) * Q) * xc + xc * c;
+  const S old_v = ((S(0.5) * x) * Q) * x + x * c;
+  const int arm = armijo_quick(v - old_v, slope, p.armijo);
+  /* iteration 1, at (xc, v) */
+  bool noimp1 = (val0 - v) < p.min_rel_improve * t_abs(val0);
+  S grad1 = Q * xc + c;
+  bool clamped1 = qp_is_clamped(p, xc, grad1, lo, hi);
+  bool small1 = t_abs(grad1) < p.min_grad;
+  /* the reference's order of tests */
+  const bool stop0 = clamped0 || small0 || ascent;
+  bool ls_failed = false;
+  if (!stop0 && arm != 0) { /* quadclamp_line_search's loop (:161-173) */
+    S step = 1;
+    bool fails = arm > 0 ? true : (v - old_v) / slope < p.armijo;
+    while (fails) {
+      step *= p.step_dec;
+      xc = clampd(x + step * search, lo, hi);
+      v = ((S(0.5) * xc) * Q) * xc + xc * c;
+      if (step < p.min_step) {
+        ls_failed = true;
+        break;
+      }
+      fails = armijo_fails(v - old_v, step * slope, p.armijo);
+    }
+    noimp1 = (val0 - v) < p.min_rel_improve * t_abs(val0);
+    grad1 = Q * xc + c;
+    clamped1 = qp_is_clamped(p, xc, grad1, lo, hi);
+    small1 = t_abs(grad1) < p.min_grad;
+  }
+  const int res0 = clamped0 ? 6 : (small0 ? 5 : 2);
+  const int res1 = ls_failed ? 2 : (noimp1 ? 4 : (clamped1 ? 6 : (small1 ? 5 : -1)));
+  const int result = stop0 ? res0 : (p.max_iter >= 1 ? res1 : -1);
+#if defined(ILQR_QP_STATS) && !defined(__CUDA_ARCH__)
+  qp_stats(result, stop0 ? 0 : arm);
+#endif
+  if (result < 0) return box_qp_scalar_loop<S>(p, Q, c, x0, lo, hi, R, Hinv);
+  const bool keep_x = stop0 || ls_failed; /* a failed line search leaves x where it was (:123-126) */
+  QPScalar<S> r;
+  r.x = keep_x ? x : xc;
+  r.R = clamped0 ? S(0) : R;
+  r.Hinv = Hinv;
+  r.v_free = keep_x ? (clamped0 ? 0 : 1) : ((!noimp1 && clamped1) ? 0 : 1);
+  r.result = result;
+  return r;
+}
+
+/* the problem in w solved by the version the backward pass uses for this m (test hook) */
 template <int M, typename S>
 ILQR_HD void box_qp(const QPParams<S> &p, QPWork<M, S> &w) {
-  if constexpr (M == 1) box_qp_scalar<S>(p, w);
-  else box_qp_generic<M, S>(p, w);
+  if constexpr (M == 1) {
+    const QPScalar<S> r = box_qp_scalar<S>(p, w.Q[0], w.c[0], w.x0[0], w.lo[0], w.hi[0]);
+    w.x[0] = r.x;
+    w.R[0] = r.R;
+    w.Hinv[0] = r.Hinv;
+    w.v_free[0] = r.v_free;
+    w.r_dim = 1;
+    w.result = r.result;
+  } else {
+    box_qp_generic<M, S>(p, w);
+  }
 }
 
 }  // namespace ilqr

@@ -23,6 +23,7 @@
 
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include "../../include/ilqr_b200.h"
 #include "../../include/ilqr_synth.h"
@@ -36,7 +37,12 @@ namespace {
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef ILQR_MIN_BLOCKS
-#define ILQR_MIN_BLOCKS 7 /* resident CTAs per SM the register allocation must allow */
+/* Resident CTAs per SM the register allocation must allow.  4 (126 registers, 16 warps per SM) is faster than 7
+ * (72 registers, the whole BASELINE batch of 4096 resident at once) even though the batch then needs a second
+ * wave: a trajectory is a serial chain, a lone warp issues in order, and under the 72-register cap ptxas sinks
+ * every shared-memory load next to its use, so each dependent step pays the full load latency (measured, one
+ * warp: 425 -> 308 us per loop trip; configs[1] solve 75.5 -> 67.1 ms). */
+#define ILQR_MIN_BLOCKS 4
 #endif
 
 enum Op { kOpInit = 0, kOpWarm = 1, kOpIterate = 2, kOpBackwardOnce = 3, kOpRolloutOnce = 4 };
@@ -145,6 +151,16 @@ __global__ void __launch_bounds__(kThreads, G == 32 ? ILQR_MIN_BLOCKS : 4) ilqr_
       }
     }
   }
+#if defined(ILQR_PHASE_CLOCKS)
+  if (a.op == kOpIterate && blockIdx.x == 0 && threadIdx.x == 0) {
+    static const char *names[16] = {"deriv_sweep", "bw_P1_W", "bw_P2_Q", "bw_P3_boxqp", "bw_P4_Vt", "bw_P5_sym", "bw_tile_load",
+                                    "bw_tile_flush", "bw_terminal", "gnorm+test", "rollout_cand_compute", "accept_test", "commit",
+                                    "lambda_sched", "roll_tile_load", "trip_head"};
+    for (int i = 0; i < 16; i++)
+      printf("phase %2d %-22s cycles %12llu  count %8llu  avg %8.1f\n", i, names[i], g_phase_clk[i], g_phase_cnt[i],
+             g_phase_cnt[i] ? (double)g_phase_clk[i] / (double)g_phase_cnt[i] : 0.0);
+  }
+#endif
 }
 
 /* per-trajectory scalars out of the state records, one thread per trajectory */
@@ -277,11 +293,22 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
 
 template <class Model, typename S>
 int launch_cd(ilqr_handle *h, int op, int n_iters, double scalar) {
+#if defined(ILQR_EXPERIMENT_BUILD) /* experiments only: acrobot f64 analytic, to keep the build short */
+  if (!(std::is_same<Model, Acrobot>::value && std::is_same<S, double>::value && h->desc.cost_deriv == ILQR_COST_ANALYTIC))
+    return fail(h, ILQR_E_INVALID, "experiment build: acrobot f64 analytic only");
+  if constexpr (std::is_same<Model, Acrobot>::value && std::is_same<S, double>::value) {
+    const bool pack16 = h->lanes == 16 || (h->lanes == 0 && h->desc.B >= 32768);
+    return pack16 ? launch_t<Model, S, kCostAnalytic, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostAnalytic, 32>(h, op, n_iters, scalar);
+  } else {
+    return ILQR_E_INVALID;
+  }
+#else
   /* two trajectories per warp once the batch can fill the schedulers that way (4 warps per scheduler on 148 SMs) */
   const bool pack = h->lanes == 16 || (h->lanes == 0 && h->desc.B >= 32768);
   if (h->desc.cost_deriv == ILQR_COST_ANALYTIC)
     return pack ? launch_t<Model, S, kCostAnalytic, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostAnalytic, 32>(h, op, n_iters, scalar);
   return pack ? launch_t<Model, S, kCostFD, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostFD, 32>(h, op, n_iters, scalar);
+#endif
 }
 template <class Model>
 int launch_s(ilqr_handle *h, int op, int n_iters, double scalar) {

@@ -110,15 +110,13 @@ struct Scratch {
   S Ct[CD == kCostFD ? kTileB * NCF : 1];    /* backward: FD cost derivatives of the tile (full layout) */
   /* one timestep */
   S x[N], u[M];         /* xs[T] and a zero control for the terminal derivatives */
-  S Cf[NCF];            /* terminal / closed-form cost derivatives, full layout */
+  S Cf[NCF];            /* terminal cost derivatives, full layout */
   S Va[N * NA];         /* [Vxx | Vx] at i+1, overwritten with i at the end of the step */
   S W[NM * NA];         /* F^T [Vxx' | Vx'] */
-  S Qxa[N * NA];        /* [Qxx | Qx] */
-  S Qua[M * NA];        /* [Qux | Qu] */
+  S Qa[NM * NA];        /* [Qxx | Qx ; Qux | Qu]: row c of the stacked variable, column b <= n */
   S Quu[M * M];
-  S Ka[M * NA];         /* [K_i | k_i] */
-  S kprev[M];
-  S Vt[N * NA];         /* [Vxx | Vx] before symmetrisation */
+  S Ka[M * NA];         /* [K_i | k_i]  (m > 1; with one control the gains stay in registers) */
+  S kprev[M];           /* (m > 1) */
   S newcost[kMaxAlpha];
   QPWork<M, S> qp;
   TrajState<S> st;
@@ -129,9 +127,14 @@ template <int N, int M, typename S>
 struct LaneRegs {
   S x[N];
   S cost;
+  S dV[2];   /* backward pass: the expected-reduction sums (lane 0's copy is the one of record) */
+  S kprev;   /* backward pass, one control: warm start of the next boxQP, kept by every lane */
 };
 
 #if defined(__CUDACC__)
+#if defined(ILQR_PHASE_CLOCKS)
+__device__ unsigned long long g_phase_clk[32], g_phase_cnt[32];
+#endif
 /* device: the calling thread is one lane; a phase ends with a warp barrier.
  *
  * stage_issue / stage_wait move one contiguous tile global -> shared with the 1-D bulk form of TMA
@@ -149,11 +152,33 @@ struct WarpExec {
   unsigned bar;         /* shared-window address of the group's mbarrier */
   unsigned phase = 0;   /* bit 0: parity to wait for; bit 1: a bulk copy is outstanding */
 
+  __device__ __forceinline__ void group_sync() {
+#if defined(UB_SYNC_CONST)
+    if constexpr (G == 32) __syncwarp();
+    else __syncwarp(mask);
+#else
+    __syncwarp(mask);
+#endif
+  }
   template <class Fn>
   __device__ __forceinline__ void lanes(Fn fn) {
     fn(lane, regs);
-    __syncwarp(mask);
+    group_sync();
   }
+  /* experiment builds only (-DILQR_PHASE_CLOCKS): cycles since the previous tick are charged to phase `id` */
+#if defined(ILQR_PHASE_CLOCKS)
+  long long last_clk = 0;
+  __device__ __forceinline__ void tick(int id) {
+    if (lane == 0) {
+      const long long now = clock64();
+      atomicAdd(&g_phase_clk[id], (unsigned long long)(now - last_clk));
+      atomicAdd(&g_phase_cnt[id], 1ULL);
+      last_clk = now;
+    }
+  }
+#else
+  __device__ __forceinline__ void tick(int) {}
+#endif
   __device__ __forceinline__ static unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
   __device__ __forceinline__ void init_barrier(unsigned long long *b) {
     bar = s32(b);
@@ -213,6 +238,7 @@ struct HostExec {
     for (int e = 0; e < count; e++) dst[e] = src[e];
   }
   void stage_wait() {}
+  void tick(int) {}
 };
 
 /* Accumulates products in index order.  The reference's sums start from zero (Eigen zero-initialises, the
@@ -372,28 +398,11 @@ struct Core {
     }
   }
 
-  /* closed-form cost derivatives of the model twin, scattered into the full layout (one lane) */
+  /* closed-form cost derivatives of the model twin in the full layout (one lane; terminal step only) */
   ILQR_HD void analytic_cost(const S *x, const S *u, bool terminal, S *cf) {
-    S cx[N], cu[M], cxx[N * N], cxu[N * M], cuu[M * M];
-    Model::cost_derivs(x, u, P.mp, terminal, cx, cu, cxx, cxu, cuu);
-#pragma unroll
-    for (int i = 0; i < N; i++) cf[i] = cx[i];
-#pragma unroll
-    for (int j = 0; j < M; j++) cf[N + j] = cu[j];
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-#pragma unroll
-      for (int j = 0; j < N; j++) cf[ix_cxx(i, j)] = cxx[i * N + j];
-#pragma unroll
-      for (int j = 0; j < M; j++) {
-        cf[ix_cxu(i, j)] = cxu[i * M + j];
-        cf[ix_cux(j, i)] = cxu[i * M + j];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < M; i++)
-#pragma unroll
-      for (int j = 0; j < M; j++) cf[ix_cuu(i, j)] = cuu[i * M + j];
+    for (int c = 0; c < NM; c++) cf[c] = Model::cost_d1(c, x, u, P.mp, terminal);
+    for (int c = 0; c < NM; c++)
+      for (int d = 0; d < NM; d++) cf[NM + c * NM + d] = Model::cost_d2(c, d, x, u, P.mp, terminal);
   }
 
   /* get_dynamics_derivatives (+ get_cost_derivatives / get_cost_2nd_derivatives in FD mode) for the
@@ -461,68 +470,121 @@ struct Core {
   /* ---- backward pass -------------------------------------------------------------------- */
 
   /* One timestep of the backward recursion for tile entry tt; returns false when the boxQP reports
-   * failure (result < 1, src/ilqr_core.cpp:371).  Every phase but the boxQP has a single code path:
-   * the value function is kept augmented, Va = [Vxx | Vx] (n x (n+1)), and so are the products
-   * that consume it, so Qx/Qu ride along as one more column of F^T Va and Vx as one more column
-   * of the Vxx update.  cf = cost derivatives of this timestep in the full layout. */
-  ILQR_HD bool backward_step(int tt, S lam, const S *cf) {
+   * failure (result < 1, src/ilqr_core.cpp:371).  The value function is kept augmented,
+   * Va = [Vxx | Vx] (n x (n+1)).  Three warp phases when there is one control, four otherwise:
+   *
+   *   A. the Q-function (:359-367) as two products with one entry per lane each: W = F^T [Vxx' | Vx'],
+   *      then Q = C + W F.  A lane needs 2n operands per entry, which it loads up front; forming a whole
+   *      row of W per lane to save the exchange was measured and is slower (6n + n^2 operands under the
+   *      register cap serialise on shared-memory latency).  The closed-form cost derivative of the
+   *      entry is evaluated in place (Model::cost_d1/_d2).
+   *   B. boxQP, gains, dV (:369-389) and the value-function update with its symmetrisation
+   *      (:391-393).  With one control the boxQP is a few dozen scalar operations, so EVERY lane
+   *      runs it in registers (same instructions, no divergence, nothing to broadcast) and goes
+   *      straight on to its own entry of Vxx / Vx: the lane of (a, b) evaluates both Vt[a][b] and
+   *      Vt[b][a] and averages them.  With several controls lane 0 solves the QP in the scratch
+   *      (phase B1) and the update is a third phase.
+   *
+   * cfd = finite-difference cost derivatives of this timestep in the full layout, or nullptr. */
+  ILQR_HD bool backward_step(int tt, S lam, const S *cfd) {
     const S *F = sc.Ft + tt * NM * N; /* F[j][r]: column j of [fx | fu] */
+    const S *xt = sc.xs + tt * N;
     const S *ut = sc.us + tt * M;
-    /* W = F^T [Vxx' | Vx']  (:359-363): column n gives Qx = cx + fx^T Vx', Qu = cu + fu^T Vx' */
-    ex.lanes([&](int lane, Lane &) {
+    /* ---- A1: W = F^T [Vxx' | Vx'], one entry per lane ---- */
+#ifndef UB_PHASE_MASK
+#define UB_PHASE_MASK 127
+#endif
+    if (UB_PHASE_MASK & 1) ex.lanes([&](int lane, Lane &) {
       for (int e = lane; e < NM * NA; e += G) {
         const int c = e / NA, b = e % NA;
-        Acc<S> acc;
+        Acc<S> w;
 #pragma unroll
-        for (int r = 0; r < N; r++) acc.add(F[c * N + r] * sc.Va[r * NA + b]);
-        sc.W[e] = acc.v;
-        if (b == N) {
-          const S q = cf[c] + acc.v;
-          if (c < N) sc.Qxa[c * NA + N] = q;
-          else sc.Qua[(c - N) * NA + N] = q;
-        }
+        for (int q = 0; q < N; q++) w.add(F[c * N + q] * sc.Va[q * NA + b]);
+        sc.W[e] = w.v;
       }
     });
-    /* Q[c][d] = C[c][d] + sum_r W[c][r] F[d][r]: Qxx, Qux, Quu (:361-363) and the regularised QuuF (:367) */
-    ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < NM * NM; e += G) {
-        const int c = e / NM, d = e % NM;
+    ex.tick(1);
+    /* ---- A2: Q[c][d] = C[c][d] + sum_r W[c][r] F[d][r]  (Qxx, Qux, Quu :361-363, QuuF :367) and
+     * Qx = cx + fx^T Vx', Qu = cu + fu^T Vx' (:359-360) from the last column of W.  Entry (c, b) of
+     * Qa = [Qxx | Qx ; Qux | Qu] goes to the lane that formed W[c][b]; m*m more entries are Quu.  One
+     * instruction stream for all of them (a lane of the vector column runs the dot product on row 0
+     * and discards it): divergent branches here cost a lone warp more than the wasted multiplies. ---- */
+    if (UB_PHASE_MASK & 2) ex.lanes([&](int lane, Lane &) {
+      S *Qa = sc.Qa;
+      for (int e = lane; e < NM * NA + M * M; e += G) {
+        const bool is_uu = e >= NM * NA;
+        const int c = is_uu ? N + (e - NM * NA) / M : e / NA;
+        const int b = is_uu ? N + (e - NM * NA) % M : e % NA;
+        const bool is_vec = !is_uu && b == N;
+        const int d = is_vec ? 0 : b;
         Acc<S> acc;
 #pragma unroll
         for (int r = 0; r < N; r++) acc.add(sc.W[c * NA + r] * F[d * N + r]);
-        const S cc = cf[NM + e];
-        const S q = cc + acc.v;
-        if (d < N) {
-          if (c < N) sc.Qxa[c * NA + d] = q;
-          else sc.Qua[(c - N) * NA + d] = q;
-        } else if (c >= N) {
-          sc.Quu[(c - N) * M + (d - N)] = q;
-          sc.qp.Q[(c - N) * M + (d - N)] = (cc + (c == d ? lam : S(0))) + acc.v;
-        }
+        const S wv = sc.W[c * NA + N];
+        S cc;
+        if (cfd) cc = is_vec ? cfd[c] : cfd[NM + c * NM + d];
+        else cc = is_vec ? Model::cost_d1(c, xt, ut, P.mp, false) : Model::cost_d2(c, d, xt, ut, P.mp, false);
+        const S q = cc + (is_vec ? wv : acc.v);
+        S *dst = is_uu ? &sc.Quu[e - NM * NA] : &Qa[e];
+        *dst = q;
+        if (is_uu) sc.qp.Q[e - NM * NA] = (cc + (c == d ? lam : S(0))) + acc.v; /* QuuF :367 */
       }
     });
-    /* boxQP, gains, dV (:369-389) — one lane; k / K go to the augmented gain Ka = [K | k] and to the tile */
-    ex.lanes([&](int lane, Lane &) {
-      if (lane != 0) return;
-      QPWork<M, S> &w = sc.qp;
-#pragma unroll
-      for (int j = 0; j < M; j++) {
-        w.c[j] = sc.Qua[j * NA + N];
-        w.x0[j] = sc.kprev[j];
-        w.lo[j] = P.u_min[j] - ut[j];
-        w.hi[j] = P.u_max[j] - ut[j];
-      }
-      box_qp<M, S>(P.qp, w);
-      if (w.result < 1) return;
-      for (int e = 0; e < M * NA; e++) sc.Ka[e] = 0;
-#pragma unroll
-      for (int j = 0; j < M; j++) sc.Ka[j * NA + N] = w.x[j];
-      if constexpr (M == 1) {
-        if (w.v_free[0]) {
-#pragma unroll
-          for (int b = 0; b < N; b++) sc.Ka[b] = (-w.Hinv[0]) * sc.Qua[b];
+    ex.tick(2);
+    if constexpr (M == 1) {
+      int result = 1;
+      /* ---- B, one control ---- */
+      if (UB_PHASE_MASK & 4) ex.lanes([&](int lane, Lane &L) {
+        const S Quu = sc.Quu[0], Qu = sc.Qa[N * NA + N];
+        const QPScalar<S> r = box_qp_scalar<S>(P.qp, sc.qp.Q[0], Qu, L.kprev, P.u_min[0] - ut[0], P.u_max[0] - ut[0]);
+        result = r.result;
+        if (r.result < 1) return;
+        const S kk = r.x;
+        const S nH = -r.Hinv;
+        const bool fr = r.v_free != 0;
+        L.dV[0] += kk * Qu;                 /* :388 */
+        L.dV[1] += ((S(0.5) * kk) * Quu) * kk; /* :389, unregularised Quu */
+        L.kprev = kk;                       /* warm start of the next boxQP (:369) */
+        /* gains (:373-385, :396-397): entry b <= n of [K | k] is kept by the lane b */
+        const S *Qua = sc.Qa + N * NA; /* [Qux | Qu] */
+        if (lane <= N) {
+          const S g = lane < N ? (fr ? nH * Qua[lane] : S(0)) : kk;
+          S *dst = lane < N ? &sc.K[tt * N + lane] : &sc.k[tt];
+          *dst = g;
         }
-      } else {
+        /* value function (:391-393): the lane of (a, b) forms Vt[a][b] and Vt[b][a] and averages them; the Vx
+         * column (b == n) runs the same instructions with k, Qu in the place of K[b], Qux[b] and copies
+         * its value (0.5 * (v + v) == v exactly) */
+        if (UB_PHASE_MASK & 64) for (int e = lane; e < N * NA; e += G) {
+          const int a = e / NA, b = e % NA;
+          const bool col = b < N;
+          const S qa = Qua[a], qb = Qua[b];
+          const S Kga = fr ? nH * qa : S(0);
+          const S Kgb = col ? (fr ? nH * qb : S(0)) : kk;
+          const S v1 = sc.Qa[a * NA + b] + (Kga * Quu) * Kgb + Kga * qb + qa * Kgb;
+          const S v2 = sc.Qa[(col ? b : 0) * NA + a] + (Kgb * Quu) * Kga + Kgb * qa + qb * Kga;
+          sc.Va[e] = S(0.5) * (v1 + (col ? v2 : v1));
+        }
+      });
+      ex.tick(3);
+      return result >= 1;
+    } else {
+      /* ---- B1, several controls: boxQP, gains, dV on one lane; k / K go to Ka = [K | k] and to the tile ---- */
+      ex.lanes([&](int lane, Lane &L) {
+        if (lane != 0) return;
+        QPWork<M, S> &w = sc.qp;
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          w.c[j] = sc.Qa[N * NA + j * NA + N];
+          w.x0[j] = sc.kprev[j];
+          w.lo[j] = P.u_min[j] - ut[j];
+          w.hi[j] = P.u_max[j] - ut[j];
+        }
+        box_qp_generic<M, S>(P.qp, w);
+        if (w.result < 1) return;
+        for (int e = 0; e < M * NA; e++) sc.Ka[e] = 0;
+#pragma unroll
+        for (int j = 0; j < M; j++) sc.Ka[j * NA + N] = w.x[j];
         const int r = w.r_dim;
         int q = 0;
         for (int j = 0; j < M; j++)
@@ -531,96 +593,91 @@ struct Core {
           for (int a = 0; a < r && a < q; a++)
             for (int b = 0; b < N; b++) {
               S acc = 0;
-              for (int c = 0; c < r && c < q; c++) acc += (-w.Hinv[a * r + c]) * sc.Qua[w.idx[c] * NA + b];
+              for (int c = 0; c < r && c < q; c++) acc += (-w.Hinv[a * r + c]) * sc.Qa[N * NA + w.idx[c] * NA + b];
               sc.Ka[w.idx[a] * NA + b] = acc;
             }
         }
-      }
-      Acc<S> a0; /* :388-389, unregularised Quu */
+        Acc<S> a0; /* :388-389, unregularised Quu */
 #pragma unroll
-      for (int j = 0; j < M; j++) a0.add(sc.Ka[j * NA + N] * sc.Qua[j * NA + N]);
-      sc.st.dV0 += a0.v;
-      Acc<S> a1;
-      S row[M];
+        for (int j = 0; j < M; j++) a0.add(sc.Ka[j * NA + N] * sc.Qa[N * NA + j * NA + N]);
+        L.dV[0] += a0.v;
+        Acc<S> a1;
+        S row[M];
 #pragma unroll
-      for (int b = 0; b < M; b++) {
-        Acc<S> acc;
-#pragma unroll
-        for (int a = 0; a < M; a++) acc.add((S(0.5) * sc.Ka[a * NA + N]) * sc.Quu[a * M + b]);
-        row[b] = acc.v;
-      }
-#pragma unroll
-      for (int b = 0; b < M; b++) a1.add(row[b] * sc.Ka[b * NA + N]);
-      sc.st.dV1 += a1.v;
-#pragma unroll
-      for (int j = 0; j < M; j++) { /* :396-397, and the warm start of the next boxQP (:369) */
-        sc.kprev[j] = sc.Ka[j * NA + N];
-        sc.k[tt * M + j] = sc.Ka[j * NA + N];
-#pragma unroll
-        for (int b = 0; b < N; b++) sc.K[(tt * M + j) * N + b] = sc.Ka[j * NA + b];
-      }
-    });
-    if (sc.qp.result < 1) return false;
-    /* [Vxx | Vx] before symmetrisation (:391-392): column b < n is Vxx[:, b], column n is Vx */
-    ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * NA; e += G) {
-        const int a = e / NA, b = e % NA;
-        S ktq[M]; /* row a of K^T Quu */
-#pragma unroll
-        for (int bb = 0; bb < M; bb++) {
+        for (int b = 0; b < M; b++) {
           Acc<S> acc;
 #pragma unroll
-          for (int c = 0; c < M; c++) acc.add(sc.Ka[c * NA + a] * sc.Quu[c * M + bb]);
-          ktq[bb] = acc.v;
+          for (int a = 0; a < M; a++) acc.add((S(0.5) * sc.Ka[a * NA + N]) * sc.Quu[a * M + b]);
+          row[b] = acc.v;
         }
-        Acc<S> t1, t2, t3;
 #pragma unroll
-        for (int c = 0; c < M; c++) t1.add(ktq[c] * sc.Ka[c * NA + b]);
+        for (int b = 0; b < M; b++) a1.add(row[b] * sc.Ka[b * NA + N]);
+        L.dV[1] += a1.v;
 #pragma unroll
-        for (int c = 0; c < M; c++) t2.add(sc.Ka[c * NA + a] * sc.Qua[c * NA + b]);
+        for (int j = 0; j < M; j++) { /* :396-397, and the warm start of the next boxQP (:369) */
+          sc.kprev[j] = sc.Ka[j * NA + N];
+          sc.k[tt * M + j] = sc.Ka[j * NA + N];
 #pragma unroll
-        for (int c = 0; c < M; c++) t3.add(sc.Qua[c * NA + a] * sc.Ka[c * NA + b]);
-        sc.Vt[e] = sc.Qxa[e] + t1.v + t2.v + t3.v;
-      }
-    });
-    /* symmetrise (:393) and roll the value function; the closed-form cost derivatives of the next
-     * timestep (tt - 1) are prepared on the last lane */
-    ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < N * NA; e += G) {
-        const int a = e / NA, b = e % NA;
-        const int bt = (b < N) ? b : a; /* column n (Vx) is copied: 0.5 * (v + v) == v exactly */
-        const int at = (b < N) ? a : N;
-        const S v1 = sc.Vt[a * NA + b];
-        const S v2 = (b < N) ? sc.Vt[bt * NA + at] : v1;
-        sc.Va[e] = S(0.5) * (v1 + v2);
-      }
-      if (CD == kCostAnalytic && lane == G - 1 && tt > 0) analytic_cost(sc.xs + (tt - 1) * N, sc.us + (tt - 1) * M, false, sc.Cf);
-    });
-    return true;
+          for (int b = 0; b < N; b++) sc.K[(tt * M + j) * N + b] = sc.Ka[j * NA + b];
+        }
+      });
+      ex.tick(3);
+      if (sc.qp.result < 1) return false;
+      /* ---- B2: [Vxx | Vx] (:391-392) and the symmetrisation (:393); column n (Vx) is copied:
+       * 0.5 * (v + v) == v exactly ---- */
+      ex.lanes([&](int lane, Lane &) {
+        for (int e = lane; e < N * NA; e += G) {
+          const int a = e / NA, b = e % NA;
+          S v[2];
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            const int aa = (side == 0 || b == N) ? a : b, bb = (side == 0 || b == N) ? b : a;
+            S ktq[M]; /* row aa of K^T Quu */
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+              Acc<S> acc;
+#pragma unroll
+              for (int c = 0; c < M; c++) acc.add(sc.Ka[c * NA + aa] * sc.Quu[c * M + j]);
+              ktq[j] = acc.v;
+            }
+            Acc<S> t1, t2, t3;
+#pragma unroll
+            for (int c = 0; c < M; c++) t1.add(ktq[c] * sc.Ka[c * NA + bb]);
+#pragma unroll
+            for (int c = 0; c < M; c++) t2.add(sc.Ka[c * NA + aa] * sc.Qa[N * NA + c * NA + bb]);
+#pragma unroll
+            for (int c = 0; c < M; c++) t3.add(sc.Qa[N * NA + c * NA + aa] * sc.Ka[c * NA + bb]);
+            v[side] = sc.Qa[aa * NA + bb] + t1.v + t2.v + t3.v;
+          }
+          sc.Va[e] = S(0.5) * (v[0] + v[1]);
+        }
+      });
+      ex.tick(4);
+      return true;
+    }
   }
 
   /* iLQR::backward_pass.  Returns the failing timestep or 0 (:371,400). */
   ILQR_HD int backward_pass(S lam) {
     const int T = P.T;
-    ex.lanes([&](int lane, Lane &) {
+    ex.lanes([&](int lane, Lane &L) {
       if (lane < N) sc.x[lane] = tr.xs[T * N + lane];
-      if (lane < M) {
-        sc.u[lane] = 0;
-        sc.kprev[lane] = tr.k[(T - 1) * M + lane]; /* :369 warm start of i = T-1: the previous pass's k[T-1] */
-      }
-      if (lane == 0) {
-        sc.st.dV0 = 0; /* :356 */
-        sc.st.dV1 = 0;
-        sc.st.n_backward++;
-      }
+      if (lane < M) sc.u[lane] = 0;
+      /* :369 warm start of i = T-1: the previous pass's k[T-1] */
+      if constexpr (M == 1) L.kprev = tr.k[T - 1];
+      else if (lane < M) sc.kprev[lane] = tr.k[(T - 1) * M + lane];
+      L.dV[0] = 0; /* :356 */
+      L.dV[1] = 0;
+      if (lane == 0) sc.st.n_backward++;
     });
     phase_terminal();
+    ex.tick(8);
     int diverged_at = -1;
     for (int ti = (T - 1) / kTileB; ti >= 0 && diverged_at < 0; ti--) {
       const int t0 = ti * kTileB;
       const int cnt = (T - t0 < kTileB) ? T - t0 : kTileB;
-      ex.stage_issue(sc.Ft, sl.F + (size_t)t0 * NM * N, cnt * NM * N, P.bulk_f != 0);
-      ex.lanes([&](int lane, Lane &) {
+      if (UB_PHASE_MASK & 16) ex.stage_issue(sc.Ft, sl.F + (size_t)t0 * NM * N, cnt * NM * N, P.bulk_f != 0);
+      if (UB_PHASE_MASK & 32) ex.lanes([&](int lane, Lane &) {
         for (int e = lane; e < cnt * N; e += G) sc.xs[e] = tr.xs[t0 * N + e];
         for (int e = lane; e < cnt * M; e += G) sc.us[e] = tr.us[t0 * M + e];
         if constexpr (CD == kCostFD) {
@@ -628,27 +685,29 @@ struct Core {
         }
       });
       ex.stage_wait();
-      if constexpr (CD == kCostAnalytic) { /* cost derivatives of the tile's first timestep (the rest are prepared step by step) */
-        ex.lanes([&](int lane, Lane &) {
-          if (lane == 0) analytic_cost(sc.xs + (cnt - 1) * N, sc.us + (cnt - 1) * M, false, sc.Cf);
-        });
-      }
+      ex.tick(6);
       int first_done = 0; /* tile entries [first_done, cnt) hold finished k / K */
       for (int tt = cnt - 1; tt >= 0; tt--) {
-        const S *cf = (CD == kCostFD) ? sc.Ct + tt * NCF : sc.Cf;
-        if (!backward_step(tt, lam, cf)) { /* the steps above this one have already written their k, K (:396-397) */
+        const S *cfd = (CD == kCostFD) ? sc.Ct + tt * NCF : nullptr;
+        if (!backward_step(tt, lam, cfd)) { /* the steps above this one have already written their k, K (:396-397) */
           diverged_at = t0 + tt;
           first_done = tt + 1;
           break;
         }
       }
       /* flush the tile's k / K and the gradient-norm terms of its timesteps (:405-412), one per lane */
-      ex.lanes([&](int lane, Lane &) {
+      if (UB_PHASE_MASK & 8) ex.lanes([&](int lane, Lane &) {
         for (int e = lane + first_done * M * N; e < cnt * M * N; e += G) tr.K[t0 * M * N + e] = sc.K[e];
         for (int e = lane + first_done * M; e < cnt * M; e += G) tr.k[t0 * M + e] = sc.k[e];
         for (int e = lane + first_done; e < cnt; e += G) sl.gterm[t0 + e] = gn_term(sc.k + e * M, sc.us + e * M);
       });
+      ex.tick(7);
     }
+    ex.lanes([&](int lane, Lane &L) {
+      if (lane != 0) return;
+      sc.st.dV0 = L.dV[0];
+      sc.st.dV1 = L.dV[1];
+    });
     if (diverged_at >= 0) return diverged_at;
     /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
     ex.lanes([&](int lane, Lane &) {
@@ -739,7 +798,9 @@ struct Core {
     });
     for (int t0 = 0; t0 < T; t0 += kTile) {
       const int cnt = (T - t0 < kTile) ? T - t0 : kTile;
+      ex.tick(10);
       load_forward_tile(t0, cnt, kRollClosed);
+      ex.tick(14);
       ex.lanes([&](int lane, Lane &L) {
         if (lane >= na) return;
         const S alpha = P.alpha[lane];
@@ -918,8 +979,10 @@ struct Core {
     trips_left--;
     /* :115-120 */
     if (sc.st.flg_change || !have_derivs) {
+      ex.tick(15);
       derivative_sweep();
       have_derivs = true;
+      ex.tick(0);
     }
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
@@ -962,8 +1025,10 @@ struct Core {
         sc.flag = 2;
       }
     });
+    ex.tick(9);
     if (sc.flag == 2) return false; /* gradient exit: `break` before iter++ */
     if (back_done) rollout_candidates();
+    ex.tick(10);
     /* the acceptance test :199-213 in the reference's serial order */
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
@@ -992,7 +1057,9 @@ struct Core {
       s.alpha = alpha;
     });
     const bool fwd_done = sc.flag == 1;
+    ex.tick(11);
     if (fwd_done) commit_candidate(sc.st.alpha_index);
+    ex.tick(12);
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
       TrajState<S> &s = sc.st;
@@ -1018,6 +1085,7 @@ struct Core {
       }
       if (!sc.flag) s.iter++;
     });
+    ex.tick(13);
     return sc.flag == 0;
   }
   ILQR_HD void op_iterate(int n_iters) {

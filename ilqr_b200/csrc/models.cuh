@@ -85,28 +85,20 @@ struct Acrobot {
     return Ks * Ks * (e0 * e0 + e1 * e1) + Kd * Kd * (e2 * e2 + e3 * e3);
   }
   /* Closed-form cost derivatives (cost_deriv == ILQR_COST_ANALYTIC; the reference only has the
-   * finite-difference path).  All outputs are fully written. */
+   * finite-difference path), one entry at a time over the stacked variable v = (x, u):
+   * cost_d1(c) = d cost / d v_c, cost_d2(c, d) = d2 cost / d v_c d v_d.  The backward pass asks
+   * for exactly the entry a lane needs, so nothing is staged through memory. */
   template <typename S>
-  ILQR_HD static void cost_derivs(const S *x, const S *u, const S *mp, bool terminal, S *cx, S *cu, S *cxx, S *cxu,
-                                  S *cuu) {
-#pragma unroll
-    for (int i = 0; i < N; i++) cx[i] = 0;
-#pragma unroll
-    for (int i = 0; i < N * N; i++) cxx[i] = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) cxu[i] = 0;
-    cu[0] = 0;
-    if (terminal) {
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        cx[i] = S(-800.0) * (mp[i] - x[i]);
-        cxx[i * N + i] = S(800.0);
-      }
-    } else {
-      const S w = S(0.1) * S(0.1);
-      cu[0] = 2 * w * u[0];
-    }
-    cuu[0] = 2 * (S(0.1) * S(0.1));
+  ILQR_HD static S cost_d1(int c, const S *x, const S *u, const S *mp, bool terminal) {
+    if (terminal) return c < N ? S(-800.0) * (mp[c] - x[c]) : S(0);
+    const S w = S(0.1) * S(0.1);
+    return c == N ? 2 * w * u[0] : S(0);
+  }
+  template <typename S>
+  ILQR_HD static S cost_d2(int c, int d, const S * /*x*/, const S * /*u*/, const S * /*mp*/, bool terminal) {
+    if (c != d) return S(0);
+    if (c == N) return 2 * (S(0.1) * S(0.1));
+    return terminal ? S(800.0) : S(0);
   }
 };
 
@@ -145,25 +137,21 @@ struct DoubleIntegrator {
     return quad(x, mp, S(10));
   }
   template <typename S>
-  ILQR_HD static void cost_derivs(const S *x, const S *u, const S *mp, bool terminal, S *cx, S *cu, S *cxx, S *cxu,
-                                  S *cuu) {
-    const S hx[4] = {S(1), S(1), S(0.2), S(0.2)};
+  ILQR_HD static S cost_d1(int c, const S *x, const S *u, const S *mp, bool terminal) {
     const S sc = terminal ? S(10) : S(1);
-#pragma unroll
-    for (int i = 0; i < N * N; i++) cxx[i] = 0;
-#pragma unroll
-    for (int i = 0; i < N * M; i++) cxu[i] = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      cx[i] = S(-2.0) * (sc * hx[i]) * (mp[i] - x[i]);
-      cxx[i * N + i] = S(2.0) * (sc * hx[i]);
+    if (c < N) {
+      const S h = c < 2 ? S(1) : S(0.2);
+      return S(-2.0) * (sc * h) * (mp[c] - x[c]);
     }
-    cu[0] = terminal ? S(0) : 2 * u[0];
-    cu[1] = terminal ? S(0) : 2 * u[1];
-    cuu[0] = 2;
-    cuu[1] = 0;
-    cuu[2] = 0;
-    cuu[3] = 2;
+    return terminal ? S(0) : 2 * u[c - N];
+  }
+  template <typename S>
+  ILQR_HD static S cost_d2(int c, int d, const S * /*x*/, const S * /*u*/, const S * /*mp*/, bool terminal) {
+    if (c != d) return S(0);
+    if (c >= N) return S(2);
+    const S sc = terminal ? S(10) : S(1);
+    const S h = c < 2 ? S(1) : S(0.2);
+    return S(2.0) * (sc * h);
   }
 };
 
