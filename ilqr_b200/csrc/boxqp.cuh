@@ -337,9 +337,14 @@ ILQR_HD bool qp_is_clamped(const QPParams<S> &p, S x, S grad, S lo, S hi) { /* :
   return (t_abs(x - lo) < p.clamp_tol && grad > 0) || (t_abs(x - hi) < p.clamp_tol && grad < 0);
 }
 
-/* the loop of boxQP as written, from the start (every exit the reference has) */
+/* the loop of boxQP as written, from the start (every exit the reference has); rare, so out of line on the device */
 template <typename S>
-ILQR_HD QPScalar<S> box_qp_scalar_loop(const QPParams<S> &p, S Q, S c, S x0, S lo, S hi, S R, S Hinv) {
+#if defined(__CUDACC__) && !defined(ILQR_QP_LOOP_INLINE)
+__host__ __device__ __noinline__
+#else
+ILQR_HD
+#endif
+QPScalar<S> box_qp_scalar_loop(const QPParams<S> &p, S Q, S c, S x0, S lo, S hi, S R, S Hinv) {
   S x = clampd(x0, lo, hi);
   S val = (x * Q) * x + x * c; /* :36, no 1/2 */
   S oldvalue = 0;
@@ -464,7 +469,7 @@ ILQR_HD QPScalar<S> box_qp_scalar(const QPParams<S> &p, S Q, S c, S x0, S lo, S 
 #if defined(ILQR_QP_STATS) && !defined(__CUDA_ARCH__)
   qp_stats(result, stop0 ? 0 : arm);
 #endif
-  if (result < 0) return box_qp_scalar_loop<S>(p, Q, c, x0, lo, hi, R, Hinv);
+  if (__builtin_expect(result < 0, 0)) return box_qp_scalar_loop<S>(p, Q, c, x0, lo, hi, R, Hinv);
   const bool keep_x = stop0 || ls_failed; /* a failed line search leaves x where it was (:123-126) */
   QPScalar<S> r;
   r.x = keep_x ? x : xc;

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, G == 32 ? ILQR_MIN_BLOCKS : 4) ilqr_
   }
 #if defined(ILQR_PHASE_CLOCKS)
   if (a.op == kOpIterate && blockIdx.x == 0 && threadIdx.x == 0) {
-    static const char *names[16] = {"deriv_sweep", "bw_P1_W", "bw_P2_Q", "bw_P3_boxqp", "bw_P4_Vt", "bw_P5_sym", "bw_tile_load",
+    static const char *names[16] = {"deriv_sweep", "bw_A1_W", "bw_A2_Q", "bw_B_boxqp+V", "bw_B2_V(m>1)", "-", "bw_tile_load",
                                     "bw_tile_flush", "bw_terminal", "gnorm+test", "rollout_cand_compute", "accept_test", "commit",
                                     "lambda_sched", "roll_tile_load", "trip_head"};
     for (int i = 0; i < 16; i++)

@@ -8,15 +8,19 @@
  *   1. derivative sweep — only when the trajectory changed (flgChange, :115-120).  The central
  *      differences of the Euler step (src/derivatives.cpp:15-26, finite_diff.h:35-47) have no
  *      dependence between timesteps, so they are NOT done inside the serial backward recursion:
- *      the T*(n+m) (timestep, variable) pairs are spread over the 32 lanes, each lane evaluating
- *      its +eps / -eps pair and writing one Jacobian column.  With finite-difference cost
+ *      they are spread over the 32 lanes — one lane per (timestep, configuration variable) for full
+ *      +eps / -eps Euler steps, one lane per timestep for the remaining variables, whose perturbed
+ *      points share the configuration-dependent part of the dynamics — each writing Jacobian columns.  With finite-difference cost
  *      derivatives (src/derivatives.cpp:29-144) the T*20 stencil outputs are spread the same way.
  *      The columns go to a per-warp buffer that stays in L2 (acrobot, T = 200: 32 KB).
- *   2. backward pass (:350-401), serial in t, five warp phases per timestep: F^T Vxx' entries one
- *      per lane; the (n+m)^2 Q-function entries one per lane (:359-367); boxQP + gains on one lane
- *      (src/boxqp.cpp, :369-389); the n + n^2 entries of Vx, Vxx one per lane (:391-392);
- *      symmetrisation (:393) and the k / K / gradient-norm-term stores.  Vx, Vxx and every
- *      intermediate live in the warp's shared-memory scratch.
+ *   2. backward pass (:350-401), serial in t, three warp phases per timestep (four when m > 1): F^T [Vxx' | Vx']
+ *      entries one per lane; the (n+m)^2 Q-function entries one per lane (:359-367); then boxQP + gains
+ *      (src/boxqp.cpp, :369-389) run by EVERY lane in registers when there is one control — same
+ *      instructions, nothing to broadcast — each lane going straight on to its own entry of Vx, Vxx with the
+ *      symmetrisation folded in (:391-393).  Vx, Vxx and the Q-function live in the warp's shared-memory
+ *      scratch.  A lone warp issues in order and a trajectory is one long dependent chain, so the phases are
+ *      written as single instruction streams (selects, no divergent branches) with their operands loaded up
+ *      front; tools/ubench_backward.cu measures them in isolation.
  *   3. line search (:184-226): the n_alpha candidate rollouts (:305-337) run concurrently, one per
  *      lane, each streaming its states/controls to a per-warp candidate buffer; the first accepted
  *      index is taken — result-identical to the reference's serial early-exit loop, because every
@@ -113,8 +117,8 @@ struct Scratch {
   S Cf[NCF];            /* terminal cost derivatives, full layout */
   S Va[N * NA];         /* [Vxx | Vx] at i+1, overwritten with i at the end of the step */
   S W[NM * NA];         /* F^T [Vxx' | Vx'] */
-  S Qa[NM * NA];        /* [Qxx | Qx ; Qux | Qu]: row c of the stacked variable, column b <= n */
-  S Quu[M * M];
+  S Qg[NM * (NM + 1)];  /* the Q-function over the stacked variable v = (x, u): Qg[c][d] = Q_{v_c v_d}, d < n + m, and
+                           Qg[c][n + m] = Q_{v_c}  (Qxx, Qxu / Qux, Quu; Qx, Qu) */
   S Ka[M * NA];         /* [K_i | k_i]  (m > 1; with one control the gains stay in registers) */
   S kprev[M];           /* (m > 1) */
   S newcost[kMaxAlpha];
@@ -152,18 +156,10 @@ struct WarpExec {
   unsigned bar;         /* shared-window address of the group's mbarrier */
   unsigned phase = 0;   /* bit 0: parity to wait for; bit 1: a bulk copy is outstanding */
 
-  __device__ __forceinline__ void group_sync() {
-#if defined(UB_SYNC_CONST)
-    if constexpr (G == 32) __syncwarp();
-    else __syncwarp(mask);
-#else
-    __syncwarp(mask);
-#endif
-  }
   template <class Fn>
   __device__ __forceinline__ void lanes(Fn fn) {
     fn(lane, regs);
-    group_sync();
+    __syncwarp(mask);
   }
   /* experiment builds only (-DILQR_PHASE_CLOCKS): cycles since the previous tick are charged to phase `id` */
 #if defined(ILQR_PHASE_CLOCKS)
@@ -199,7 +195,7 @@ struct WarpExec {
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* earlier generic reads of the destination */
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+        asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
                      "l"(src), "r"(bytes), "r"(bar)
                      : "memory");
       }
@@ -271,6 +267,9 @@ struct Core {
   using Sc = Scratch<N, M, S, CD>;
   using Lane = LaneRegs<N, M, S>;
   static constexpr int NA = Sc::NA, NCF = Sc::NCF;
+  static constexpr int NQ = NM + 1; /* row length of Scratch::Qg */
+  /* column of Qg for column b of an x-indexed matrix augmented with its vector (b == n: the gradient) */
+  ILQR_HD static int qcol(int b) { return b < N ? b : NM; }
 
   const SolveParams<S> &P;
   Sc &sc;
@@ -406,29 +405,74 @@ struct Core {
   }
 
   /* get_dynamics_derivatives (+ get_cost_derivatives / get_cost_2nd_derivatives in FD mode) for the
-   * whole horizon, parallel over (timestep, variable): lane <- task, each task the +eps / -eps pair
-   * of finite_diff_jacobian (finite_diff.h:35-47) for one column. */
+   * whole horizon, parallel over the lanes: every column of [fx | fu] is the +eps / -eps pair of
+   * finite_diff_jacobian (finite_diff.h:35-47) on the Euler step.  Two passes:
+   *   A. one lane per (timestep, configuration variable): two full Euler steps (a perturbed angle changes the
+   *      trigonometry, the mass matrix, everything);
+   *   B. one lane per timestep for all the other variables (velocities, controls): the model's
+   *      configuration-dependent part is formed once and shared by the 2 (n + m - nq) perturbed points, which
+   *      then cost a few dozen operations each — same operands, same operations, same results as full steps. */
+  static constexpr int kNumConfigVars = ((Model::kConfigVars >> 0) & 1) + ((Model::kConfigVars >> 1) & 1) +
+                                        ((Model::kConfigVars >> 2) & 1) + ((Model::kConfigVars >> 3) & 1) +
+                                        ((Model::kConfigVars >> 4) & 1) + ((Model::kConfigVars >> 5) & 1) +
+                                        ((Model::kConfigVars >> 6) & 1) + ((Model::kConfigVars >> 7) & 1);
+  ILQR_HD static bool is_config_var(int j) { return j < N && ((Model::kConfigVars >> j) & 1u) != 0; }
+  ILQR_HD static int nth_config_var(int q) { /* index of the q-th set bit */
+    int j = 0;
+    for (int seen = 0; j < N; j++)
+      if ((Model::kConfigVars >> j) & 1u) {
+        if (seen == q) break;
+        seen++;
+      }
+    return j;
+  }
+
   ILQR_HD void derivative_sweep() {
     const int T = P.T;
-    const int n_dyn = T * NM;
-    for (int base = 0; base < n_dyn; base += G) {
+    if constexpr (kNumConfigVars > 0) {
+      const int n_a = T * kNumConfigVars;
+      for (int base = 0; base < n_a; base += G) {
+        ex.lanes([&](int lane, Lane &) {
+          const int task = base + lane;
+          if (task >= n_a) return;
+          const int t = task / kNumConfigVars, j = nth_config_var(task - t * kNumConfigVars);
+          S x[N], u[M], xa[N], fp[N], fm[N];
+#pragma unroll
+          for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
+#pragma unroll
+          for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
+          perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
+          integrate<Model, S>(xa, u, P.mp, P.dt, fp);
+          perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
+          integrate<Model, S>(xa, u, P.mp, P.dt, fm);
+#pragma unroll
+          for (int r = 0; r < N; r++) sl.F[((size_t)t * NM + j) * N + r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+        });
+      }
+    }
+    for (int base = 0; base < T; base += G) {
       ex.lanes([&](int lane, Lane &) {
-        const int task = base + lane;
-        if (task >= n_dyn) return;
-        const int t = task / NM, j = task - t * NM;
+        const int t = base + lane;
+        if (t >= T) return;
         S x[N], u[M], xa[N], ua[M], fp[N], fm[N];
 #pragma unroll
         for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
 #pragma unroll
         for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
-        perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
-        perturb<M>(u, j - N, P.fd_eps, -1, S(0), ua);
-        integrate<Model, S>(xa, ua, P.mp, P.dt, fp);
-        perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
-        perturb<M>(u, j - N, -P.fd_eps, -1, S(0), ua);
-        integrate<Model, S>(xa, ua, P.mp, P.dt, fm);
+        typename Model::template Config<S> cf;
+        Model::configure(x, P.mp, cf);
 #pragma unroll
-        for (int r = 0; r < N; r++) sl.F[(size_t)task * N + r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+        for (int j = 0; j < NM; j++) {
+          if (is_config_var(j)) continue;
+          perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
+          perturb<M>(u, j - N, P.fd_eps, -1, S(0), ua);
+          integrate_cfg<Model, S>(cf, xa, ua, P.mp, P.dt, fp);
+          perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
+          perturb<M>(u, j - N, -P.fd_eps, -1, S(0), ua);
+          integrate_cfg<Model, S>(cf, xa, ua, P.mp, P.dt, fm);
+#pragma unroll
+          for (int r = 0; r < N; r++) sl.F[((size_t)t * NM + j) * N + r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+        }
       });
     }
     if constexpr (CD == kCostFD) {
@@ -490,52 +534,46 @@ struct Core {
     const S *F = sc.Ft + tt * NM * N; /* F[j][r]: column j of [fx | fu] */
     const S *xt = sc.xs + tt * N;
     const S *ut = sc.us + tt * M;
-    /* ---- A1: W = F^T [Vxx' | Vx'], one entry per lane ---- */
-#ifndef UB_PHASE_MASK
-#define UB_PHASE_MASK 127
-#endif
-    if (UB_PHASE_MASK & 1) ex.lanes([&](int lane, Lane &) {
+    /* ---- A1: W = F^T [Vxx' | Vx'], one entry per lane.  The last column is Qx / Qu already but for the cost
+     * gradient (:359-360): its lanes add that and store to Qa instead (same instructions, selected operands) ---- */
+    ex.lanes([&](int lane, Lane &) {
       for (int e = lane; e < NM * NA; e += G) {
         const int c = e / NA, b = e % NA;
+        const bool is_vec = b == N;
         Acc<S> w;
 #pragma unroll
         for (int q = 0; q < N; q++) w.add(F[c * N + q] * sc.Va[q * NA + b]);
-        sc.W[e] = w.v;
+        const S c1 = cfd ? cfd[c] : Model::cost_d1(c, xt, ut, P.mp, false);
+        S *dst = is_vec ? &sc.Qg[c * NQ + NM] : &sc.W[e];
+        *dst = is_vec ? c1 + w.v : w.v;
       }
     });
     ex.tick(1);
-    /* ---- A2: Q[c][d] = C[c][d] + sum_r W[c][r] F[d][r]  (Qxx, Qux, Quu :361-363, QuuF :367) and
-     * Qx = cx + fx^T Vx', Qu = cu + fu^T Vx' (:359-360) from the last column of W.  Entry (c, b) of
-     * Qa = [Qxx | Qx ; Qux | Qu] goes to the lane that formed W[c][b]; m*m more entries are Quu.  One
-     * instruction stream for all of them (a lane of the vector column runs the dot product on row 0
-     * and discards it): divergent branches here cost a lone warp more than the wasted multiplies. ---- */
-    if (UB_PHASE_MASK & 2) ex.lanes([&](int lane, Lane &) {
-      S *Qa = sc.Qa;
-      for (int e = lane; e < NM * NA + M * M; e += G) {
-        const bool is_uu = e >= NM * NA;
-        const int c = is_uu ? N + (e - NM * NA) / M : e / NA;
-        const int b = is_uu ? N + (e - NM * NA) % M : e % NA;
-        const bool is_vec = !is_uu && b == N;
-        const int d = is_vec ? 0 : b;
+    /* ---- A2: Q[c][d] = C[c][d] + sum_r W[c][r] F[d][r] over the whole stacked variable (Qxx, Qux, Quu :361-363; the
+     * Qxu block is computed too and never read: one instruction stream, because a divergent branch costs a lone
+     * warp more than the wasted multiplies); the Quu lanes also store the regularised QuuF (:367) ---- */
+    ex.lanes([&](int lane, Lane &) {
+      for (int e = lane; e < NM * NM; e += G) {
+        const int c = e / NM, d = e % NM;
         Acc<S> acc;
 #pragma unroll
         for (int r = 0; r < N; r++) acc.add(sc.W[c * NA + r] * F[d * N + r]);
-        const S wv = sc.W[c * NA + N];
-        S cc;
-        if (cfd) cc = is_vec ? cfd[c] : cfd[NM + c * NM + d];
-        else cc = is_vec ? Model::cost_d1(c, xt, ut, P.mp, false) : Model::cost_d2(c, d, xt, ut, P.mp, false);
-        const S q = cc + (is_vec ? wv : acc.v);
-        S *dst = is_uu ? &sc.Quu[e - NM * NA] : &Qa[e];
-        *dst = q;
-        if (is_uu) sc.qp.Q[e - NM * NA] = (cc + (c == d ? lam : S(0))) + acc.v; /* QuuF :367 */
+        const S cc = cfd ? cfd[NM + e] : Model::cost_d2(c, d, xt, ut, P.mp, false);
+        sc.Qg[c * NQ + d] = cc + acc.v;
+        if (c >= N && d >= N) sc.qp.Q[(c - N) * M + (d - N)] = (cc + (c == d ? lam : S(0))) + acc.v;
       }
     });
     ex.tick(2);
     if constexpr (M == 1) {
       int result = 1;
       /* ---- B, one control ---- */
-      if (UB_PHASE_MASK & 4) ex.lanes([&](int lane, Lane &L) {
-        const S Quu = sc.Quu[0], Qu = sc.Qa[N * NA + N];
+      ex.lanes([&](int lane, Lane &L) {
+        const S Quu = sc.Qg[N * NQ + N], Qu = sc.Qg[N * NQ + NM];
+        /* operands of this lane's value-function entry, loaded before the boxQP so that they are in flight behind it */
+        const S *Qua = sc.Qg + N * NQ; /* [Qux | Quu | Qu] */
+        const int e0 = lane < N * NA ? lane : 0, a0 = e0 / NA, b0 = e0 % NA;
+        const S qa0 = Qua[a0], qb0 = Qua[qcol(b0)], qab0 = sc.Qg[a0 * NQ + qcol(b0)], qba0 = sc.Qg[(b0 < N ? b0 : 0) * NQ + a0];
+        const S qg0 = Qua[lane < N ? lane : 0];
         const QPScalar<S> r = box_qp_scalar<S>(P.qp, sc.qp.Q[0], Qu, L.kprev, P.u_min[0] - ut[0], P.u_max[0] - ut[0]);
         result = r.result;
         if (r.result < 1) return;
@@ -546,23 +584,24 @@ struct Core {
         L.dV[1] += ((S(0.5) * kk) * Quu) * kk; /* :389, unregularised Quu */
         L.kprev = kk;                       /* warm start of the next boxQP (:369) */
         /* gains (:373-385, :396-397): entry b <= n of [K | k] is kept by the lane b */
-        const S *Qua = sc.Qa + N * NA; /* [Qux | Qu] */
         if (lane <= N) {
-          const S g = lane < N ? (fr ? nH * Qua[lane] : S(0)) : kk;
+          const S g = lane < N ? (fr ? nH * qg0 : S(0)) : kk;
           S *dst = lane < N ? &sc.K[tt * N + lane] : &sc.k[tt];
           *dst = g;
         }
         /* value function (:391-393): the lane of (a, b) forms Vt[a][b] and Vt[b][a] and averages them; the Vx
          * column (b == n) runs the same instructions with k, Qu in the place of K[b], Qux[b] and copies
          * its value (0.5 * (v + v) == v exactly) */
-        if (UB_PHASE_MASK & 64) for (int e = lane; e < N * NA; e += G) {
+        for (int e = lane; e < N * NA; e += G) {
           const int a = e / NA, b = e % NA;
           const bool col = b < N;
-          const S qa = Qua[a], qb = Qua[b];
+          const bool first = e == lane; /* G >= n (n + 1) lanes: the only pass, operands already loaded */
+          const S qa = first ? qa0 : Qua[a], qb = first ? qb0 : Qua[qcol(b)];
+          const S qab = first ? qab0 : sc.Qg[a * NQ + qcol(b)], qba = first ? qba0 : sc.Qg[(col ? b : 0) * NQ + a];
           const S Kga = fr ? nH * qa : S(0);
           const S Kgb = col ? (fr ? nH * qb : S(0)) : kk;
-          const S v1 = sc.Qa[a * NA + b] + (Kga * Quu) * Kgb + Kga * qb + qa * Kgb;
-          const S v2 = sc.Qa[(col ? b : 0) * NA + a] + (Kgb * Quu) * Kga + Kgb * qa + qb * Kga;
+          const S v1 = qab + (Kga * Quu) * Kgb + Kga * qb + qa * Kgb;
+          const S v2 = qba + (Kgb * Quu) * Kga + Kgb * qa + qb * Kga;
           sc.Va[e] = S(0.5) * (v1 + (col ? v2 : v1));
         }
       });
@@ -575,7 +614,7 @@ struct Core {
         QPWork<M, S> &w = sc.qp;
 #pragma unroll
         for (int j = 0; j < M; j++) {
-          w.c[j] = sc.Qa[N * NA + j * NA + N];
+          w.c[j] = sc.Qg[(N + j) * NQ + NM];
           w.x0[j] = sc.kprev[j];
           w.lo[j] = P.u_min[j] - ut[j];
           w.hi[j] = P.u_max[j] - ut[j];
@@ -593,13 +632,13 @@ struct Core {
           for (int a = 0; a < r && a < q; a++)
             for (int b = 0; b < N; b++) {
               S acc = 0;
-              for (int c = 0; c < r && c < q; c++) acc += (-w.Hinv[a * r + c]) * sc.Qa[N * NA + w.idx[c] * NA + b];
+              for (int c = 0; c < r && c < q; c++) acc += (-w.Hinv[a * r + c]) * sc.Qg[(N + w.idx[c]) * NQ + b];
               sc.Ka[w.idx[a] * NA + b] = acc;
             }
         }
         Acc<S> a0; /* :388-389, unregularised Quu */
 #pragma unroll
-        for (int j = 0; j < M; j++) a0.add(sc.Ka[j * NA + N] * sc.Qa[N * NA + j * NA + N]);
+        for (int j = 0; j < M; j++) a0.add(sc.Ka[j * NA + N] * sc.Qg[(N + j) * NQ + NM]);
         L.dV[0] += a0.v;
         Acc<S> a1;
         S row[M];
@@ -607,7 +646,7 @@ struct Core {
         for (int b = 0; b < M; b++) {
           Acc<S> acc;
 #pragma unroll
-          for (int a = 0; a < M; a++) acc.add((S(0.5) * sc.Ka[a * NA + N]) * sc.Quu[a * M + b]);
+          for (int a = 0; a < M; a++) acc.add((S(0.5) * sc.Ka[a * NA + N]) * sc.Qg[(N + a) * NQ + N + b]);
           row[b] = acc.v;
         }
 #pragma unroll
@@ -637,17 +676,17 @@ struct Core {
             for (int j = 0; j < M; j++) {
               Acc<S> acc;
 #pragma unroll
-              for (int c = 0; c < M; c++) acc.add(sc.Ka[c * NA + aa] * sc.Quu[c * M + j]);
+              for (int c = 0; c < M; c++) acc.add(sc.Ka[c * NA + aa] * sc.Qg[(N + c) * NQ + N + j]);
               ktq[j] = acc.v;
             }
             Acc<S> t1, t2, t3;
 #pragma unroll
             for (int c = 0; c < M; c++) t1.add(ktq[c] * sc.Ka[c * NA + bb]);
 #pragma unroll
-            for (int c = 0; c < M; c++) t2.add(sc.Ka[c * NA + aa] * sc.Qa[N * NA + c * NA + bb]);
+            for (int c = 0; c < M; c++) t2.add(sc.Ka[c * NA + aa] * sc.Qg[(N + c) * NQ + qcol(bb)]);
 #pragma unroll
-            for (int c = 0; c < M; c++) t3.add(sc.Qa[N * NA + c * NA + aa] * sc.Ka[c * NA + bb]);
-            v[side] = sc.Qa[aa * NA + bb] + t1.v + t2.v + t3.v;
+            for (int c = 0; c < M; c++) t3.add(sc.Qg[(N + c) * NQ + aa] * sc.Ka[c * NA + bb]);
+            v[side] = sc.Qg[aa * NQ + qcol(bb)] + t1.v + t2.v + t3.v;
           }
           sc.Va[e] = S(0.5) * (v[0] + v[1]);
         }
@@ -676,8 +715,8 @@ struct Core {
     for (int ti = (T - 1) / kTileB; ti >= 0 && diverged_at < 0; ti--) {
       const int t0 = ti * kTileB;
       const int cnt = (T - t0 < kTileB) ? T - t0 : kTileB;
-      if (UB_PHASE_MASK & 16) ex.stage_issue(sc.Ft, sl.F + (size_t)t0 * NM * N, cnt * NM * N, P.bulk_f != 0);
-      if (UB_PHASE_MASK & 32) ex.lanes([&](int lane, Lane &) {
+      ex.stage_issue(sc.Ft, sl.F + (size_t)t0 * NM * N, cnt * NM * N, P.bulk_f != 0);
+      ex.lanes([&](int lane, Lane &) {
         for (int e = lane; e < cnt * N; e += G) sc.xs[e] = tr.xs[t0 * N + e];
         for (int e = lane; e < cnt * M; e += G) sc.us[e] = tr.us[t0 * M + e];
         if constexpr (CD == kCostFD) {
@@ -696,7 +735,7 @@ struct Core {
         }
       }
       /* flush the tile's k / K and the gradient-norm terms of its timesteps (:405-412), one per lane */
-      if (UB_PHASE_MASK & 8) ex.lanes([&](int lane, Lane &) {
+      ex.lanes([&](int lane, Lane &) {
         for (int e = lane + first_done * M * N; e < cnt * M * N; e += G) tr.K[t0 * M * N + e] = sc.K[e];
         for (int e = lane + first_done * M; e < cnt * M; e += G) tr.k[t0 * M + e] = sc.k[e];
         for (int e = lane + first_done; e < cnt; e += G) sl.gterm[t0 + e] = gn_term(sc.k + e * M, sc.us + e * M);

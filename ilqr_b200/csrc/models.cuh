@@ -42,33 +42,61 @@ struct Acrobot {
    * (I1 = I2 = l1 = l2 = m1 = m2 = 1, lc = 0.5, g = 9.81).  The 2x2 inverse is the closed form
    * Eigen uses for fixed-size 2x2 (Eigen/src/LU/InverseImpl.h:76-94).  The three sincos
    * (of q2, q1, q1 + q2; trig.cuh) are independent, which the instruction scheduler exploits. */
+  /* The part of the dynamics that depends on the configuration q = (x[0], x[1]) alone: the trigonometry, the
+   * inverse of H and G.  The finite-difference sweep perturbs one variable at a time, and for the velocities
+   * and the control this part is the same for every perturbed point of a timestep, so it is formed once
+   * (Core::derivative_sweep); dynamics() below is configure() followed by dynamics_cfg(), statement for
+   * statement what it was as one function. */
+  static constexpr unsigned kConfigVars = 0x3; /* bit i set: the Config depends on x[i] */
   template <typename S>
-  ILQR_HD static void dynamics(const S *x, const S *u, const S * /*mp*/, S *dx) {
-    const S I1 = 1, I2 = 1, l1 = 1, l2 = 1, m1 = 1, m2 = 1, g = S(9.81);
+  struct Config {
+    S s2, Hi00, Hi01, Hi10, Hi11, G0, G1;
+  };
+  template <typename S>
+  ILQR_HD static void configure(const S *x, const S * /*mp*/, Config<S> &cf) {
+    const S I1 = 1, I2 = 1, l1 = 1, m1 = 1, m2 = 1, g = S(9.81);
+    const S l2 = 1;
     const S lc1 = S(0.5) * l1, lc2 = S(0.5) * l2;
-    const S q0 = x[0], q1 = x[1], qd0 = x[2], qd1 = x[3];
+    const S q0 = x[0], q1 = x[1];
     S sn[3], cs[3];
     sincos_det3(q1, q0, q0 + q1, sn, cs);
-    const S c2 = cs[0], s2 = sn[0], s1 = sn[1], s1p2 = sn[2];
+    const S c2 = cs[0], s1 = sn[1], s1p2 = sn[2];
+    cf.s2 = sn[0];
     const S H00 = I1 + I2 + m2 * l1 * l1 + 2 * m2 * l1 * lc2 * c2;
     const S H01 = I2 + m2 * l1 * lc2 * c2;
     const S H10 = I2 + m2 * l1 * lc2 * c2;
     const S H11 = I2;
+    cf.G0 = m1 * g * lc1 * s1 + m2 * g * (l1 * s1 + lc2 * s1p2);
+    cf.G1 = m2 * g * lc2 * s1p2;
+    const S det = H00 * H11 - H10 * H01;
+    const S invdet = S(1) / det;
+    cf.Hi00 = H11 * invdet;
+    cf.Hi10 = -H10 * invdet;
+    cf.Hi01 = -H01 * invdet;
+    cf.Hi11 = H00 * invdet;
+  }
+  template <typename S>
+  ILQR_HD static void dynamics_cfg(const Config<S> &cf, const S *x, const S *u, const S * /*mp*/, S *dx) {
+    const S l1 = 1, l2 = 1, m2 = 1;
+    const S lc2 = S(0.5) * l2;
+    const S qd0 = x[2], qd1 = x[3];
+    const S s2 = cf.s2;
     const S C00 = -2 * m2 * l1 * lc2 * s2 * qd1;
     const S C01 = -m2 * l2 * lc2 * s2 * qd1;
     const S C10 = m2 * l1 * lc2 * s2 * qd0;
     const S C11 = 0;
-    const S G0 = m1 * g * lc1 * s1 + m2 * g * (l1 * s1 + lc2 * s1p2);
-    const S G1 = m2 * g * lc2 * s1p2;
-    const S r0 = (S(0) - (C00 * qd0 + C01 * qd1)) - G0; /* Vector2d(0,u) - C*qdot - G */
-    const S r1 = (u[0] - (C10 * qd0 + C11 * qd1)) - G1;
-    const S det = H00 * H11 - H10 * H01;
-    const S invdet = S(1) / det;
-    const S Hi00 = H11 * invdet, Hi10 = -H10 * invdet, Hi01 = -H01 * invdet, Hi11 = H00 * invdet;
+    const S r0 = (S(0) - (C00 * qd0 + C01 * qd1)) - cf.G0; /* Vector2d(0,u) - C*qdot - G */
+    const S r1 = (u[0] - (C10 * qd0 + C11 * qd1)) - cf.G1;
     dx[0] = qd0;
     dx[1] = qd1;
-    dx[2] = Hi00 * r0 + Hi01 * r1;
-    dx[3] = Hi10 * r0 + Hi11 * r1;
+    dx[2] = cf.Hi00 * r0 + cf.Hi01 * r1;
+    dx[3] = cf.Hi10 * r0 + cf.Hi11 * r1;
+  }
+  template <typename S>
+  ILQR_HD static void dynamics(const S *x, const S *u, const S *mp, S *dx) {
+    Config<S> cf;
+    configure(x, mp, cf);
+    dynamics_cfg(cf, x, u, mp, dx);
   }
   /* Acrobot::cost :83-92 — Ks = Kd = 0, Kr = 0.1 */
   template <typename S>
@@ -92,13 +120,13 @@ struct Acrobot {
   ILQR_HD static S cost_d1(int c, const S *x, const S *u, const S *mp, bool terminal) {
     if (terminal) return c < N ? S(-800.0) * (mp[c] - x[c]) : S(0);
     const S w = S(0.1) * S(0.1);
-    return c == N ? 2 * w * u[0] : S(0);
+    const S cu = 2 * w * u[0]; /* unconditional: a select, not a branch around the load */
+    return c == N ? cu : S(0);
   }
   template <typename S>
   ILQR_HD static S cost_d2(int c, int d, const S * /*x*/, const S * /*u*/, const S * /*mp*/, bool terminal) {
-    if (c != d) return S(0);
-    if (c == N) return 2 * (S(0.1) * S(0.1));
-    return terminal ? S(800.0) : S(0);
+    const S diag = c == N ? 2 * (S(0.1) * S(0.1)) : (terminal ? S(800.0) : S(0));
+    return c == d ? diag : S(0);
   }
 };
 
@@ -117,6 +145,13 @@ struct DoubleIntegrator {
     dx[2] = u[0] / mass;
     dx[3] = u[1] / mass;
   }
+  static constexpr unsigned kConfigVars = 0; /* nothing to share between perturbed points */
+  template <typename S>
+  struct Config {};
+  template <typename S>
+  ILQR_HD static void configure(const S *, const S *, Config<S> &) {}
+  template <typename S>
+  ILQR_HD static void dynamics_cfg(const Config<S> &, const S *x, const S *u, const S *mp, S *dx) { dynamics(x, u, mp, dx); }
   template <typename S>
   ILQR_HD static S quad(const S *x, const S *mp, S scale) {
     const S hx[4] = {S(1), S(1), S(0.2), S(0.2)};
@@ -165,6 +200,14 @@ template <class Model, typename S>
 ILQR_HD_DYN void integrate(const S *x, const S *u, const S *mp, S dt, S *x1) {
   S dx[Model::N];
   Model::dynamics(x, u, mp, dx);
+#pragma unroll
+  for (int i = 0; i < Model::N; i++) x1[i] = x[i] + dx[i] * dt;
+}
+/* the same with the configuration-dependent part already formed */
+template <class Model, typename S>
+ILQR_HD void integrate_cfg(const typename Model::template Config<S> &cf, const S *x, const S *u, const S *mp, S dt, S *x1) {
+  S dx[Model::N];
+  Model::dynamics_cfg(cf, x, u, mp, dx);
 #pragma unroll
   for (int i = 0; i < Model::N; i++) x1[i] = x[i] + dx[i] * dt;
 }

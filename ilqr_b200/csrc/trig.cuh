@@ -91,6 +91,17 @@ ILQR_HD void sincos_core(double x, double *sn, double *cs) {
   *cs = ((n + 1) & 2) ? -b : b;
 }
 
+/* The platform's sincos for arguments outside the range of sincos_core.  Out of line on the device: it is never
+ * reached by a sane trajectory, and inlined (several hundred instructions of Payne-Hanek reduction at every call
+ * site) it sat between the hot instructions and cost instruction-cache misses (profiles/r1j: 13 % of the stall
+ * samples were "no instruction"). */
+#if defined(__CUDACC__) && defined(ILQR_SINCOS_SLOW_NOINLINE)
+__host__ __device__ __noinline__
+#else
+ILQR_HD
+#endif
+void sincos_slow(double x, double *sn, double *cs) { ::sincos(x, sn, cs); }
+
 ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
 #if defined(ILQR_TRIG_LIBM) && !defined(__CUDACC__)
   /* tests/emu only: the platform libm, to compare the kernel source bit for bit with the oracle */
@@ -98,8 +109,8 @@ ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
   *cs = ::cos(x);
   return;
 #endif
-  if (!sincos_in_range(x)) {
-    ::sincos(x, sn, cs);
+  if (__builtin_expect(!sincos_in_range(x), 0)) {
+    sincos_slow(x, sn, cs);
     return;
   }
   sincos_core(x, sn, cs);
@@ -203,7 +214,7 @@ ILQR_HD void sincos_detN(const double *x, double *sn, double *cs) {
   bool ok = true;
 #pragma unroll
   for (int i = 0; i < K; i++) ok = ok && sincos_in_range(x[i]);
-  if (!ok) {
+  if (__builtin_expect(!ok, 0)) {
     for (int i = 0; i < K; i++) sincos_det(x[i], sn + i, cs + i);
   }
 }

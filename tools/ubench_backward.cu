@@ -1,6 +1,7 @@
 // One warp, one trajectory: cycles of Core::derivative_sweep / backward_pass / rollout_candidates measured with
 // clock64 inside the kernel (experiment; not part of the product).
-// nvcc -O3 -fmad=false -std=c++17 -gencode arch=compute_100a,code=sm_100a -maxrregcount=72 -I ilqr_b200/csrc -I include -o /tmp/ubw tools/ubench_backward.cu
+// nvcc -O3 -fmad=false -std=c++17 -gencode arch=compute_100a,code=sm_100a [-DUB_MINB=4] -I ilqr_b200/csrc -I include -o /tmp/ubw tools/ubench_backward.cu
+// UB_MINB = resident CTAs per SM in __launch_bounds__ (7: 72 registers, 4: 126); argv[1] = 0 disables the bulk (TMA) tile copy.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
