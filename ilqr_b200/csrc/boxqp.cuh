@@ -304,13 +304,14 @@ struct QPScalar {
 #if defined(ILQR_QP_STATS) && !defined(__CUDA_ARCH__)
 #include <stdio.h>
 #include <stdlib.h>
-static long g_qp_calls, g_qp_fast[8], g_qp_slow_arm[3], g_qp_bt, g_qp_loop_iters;
+static long g_qp_calls, g_qp_fast[8], g_qp_slow_arm[3], g_qp_bt, g_qp_c0;
 static void qp_stats_print() {
-  fprintf(stderr, "qp calls %ld fast results [2]=%ld [4]=%ld [5]=%ld [6]=%ld; slow: armijo-fail %ld ambiguous %ld third-iteration %ld; backtracks %ld loop iters %ld\n",
-          g_qp_calls, g_qp_fast[2], g_qp_fast[4], g_qp_fast[5], g_qp_fast[6], g_qp_slow_arm[1], g_qp_slow_arm[2], g_qp_slow_arm[0], g_qp_bt, g_qp_loop_iters);
+  fprintf(stderr, "qp calls %ld fast results [2]=%ld [4]=%ld [5]=%ld [6]=%ld; slow: armijo-fail %ld ambiguous %ld third-iteration %ld; backtracks %ld clamped-at-once %ld\n",
+          g_qp_calls, g_qp_fast[2], g_qp_fast[4], g_qp_fast[5], g_qp_fast[6], g_qp_slow_arm[1], g_qp_slow_arm[2], g_qp_slow_arm[0], g_qp_bt, g_qp_c0);
 }
 static void qp_stats(int result, int arm) {
   if (g_qp_calls++ == 0) atexit(qp_stats_print);
+  if (arm == 99) g_qp_c0++;
   if (result >= 0) g_qp_fast[result & 7]++;
   else g_qp_slow_arm[arm < 0 ? 2 : arm]++;
 }
@@ -423,8 +424,22 @@ ILQR_HD QPScalar<S> box_qp_scalar(const QPParams<S> &p, S Q, S c, S x0, S lo, S 
   /* iteration 0 */
   const S x = clampd(x0, lo, hi);
   const S grad0 = Q * x + c;
-  const S val0 = (x * Q) * x + x * c; /* :36, no 1/2 */
   const bool clamped0 = qp_is_clamped(p, x, grad0, lo, hi);
+  if (clamped0) { /* "all clamped" at once (:74-77): 43 % of the calls of a solve — the warm start is the previous
+                     timestep's k, which sat on the bound too — and none of what follows is needed (the gains of a
+                     clamped control are zero, the factor is never formed) */
+#if defined(ILQR_QP_STATS) && !defined(__CUDA_ARCH__)
+    qp_stats(6, 99);
+#endif
+    QPScalar<S> r;
+    r.x = x;
+    r.R = S(0);
+    r.Hinv = S(0);
+    r.v_free = 0;
+    r.result = 6;
+    return r;
+  }
+  const S val0 = (x * Q) * x + x * c; /* :36, no 1/2 */
   const bool small0 = t_abs(grad0) < p.min_grad;
   const S gc0 = Q * (x * S(0)) + c;
   const S R = (Q <= 0) ? Q : t_sqrt(Q); /* Eigen LLT leaves a non-positive pivot as it is */

@@ -138,7 +138,10 @@ ILQR_HD void sincos_coreN(const double *x, double *sn, double *cs) {
 #else
   const double *tab = kTrigHost;
 #endif
-  const double invpio2 = tab[0], pio2_1 = tab[1], pio2_2 = tab[2], pio2_2t = tab[3];
+  /* the four reduction constants as immediates: they head the dependency chain, and a constant-memory load there
+   * is exposed latency (profiles/r1k: 3.9 % of the stall samples sat on the first multiply) */
+  const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00, pio2_2 = 6.07710050630396597660e-11,
+               pio2_2t = 2.02226624879595063154e-21;
   const double S1 = tab[4], S2 = tab[5], S3 = tab[6], S4 = tab[7], S5 = tab[8], S6 = tab[9];
   const double C1 = tab[10], C2 = tab[11], C3 = tab[12], C4 = tab[13], C5 = tab[14], C6 = tab[15];
   double fn[K], t[K], w[K], r[K], y0[K], y1[K], z[K], v[K], ps[K], pc[K], ks[K], kc[K], hz[K], wc[K];
