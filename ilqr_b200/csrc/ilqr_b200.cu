@@ -61,10 +61,11 @@ struct KArgs {
   S scalar; /* lambda (backward_once) or alpha (rollout_once) */
 };
 
-/* shared memory of one warp: its scratch, then T gradient-norm terms; 16-byte granules */
+/* shared memory of one lane group: its scratch, then T gradient-norm terms, then (in the last 16-byte granule, which
+ * nothing else may touch: a stray store into an mbarrier word corrupts its phase) the group's mbarrier */
 template <class Sc, typename S>
 __host__ __device__ inline size_t warp_smem_bytes(int T) {
-  return (sizeof(Sc) + (size_t)T * sizeof(S) + sizeof(unsigned long long) + 15) & ~(size_t)15;
+  return ((sizeof(Sc) + (size_t)T * sizeof(S) + 15) & ~(size_t)15) + 16;
 }
 
 /* G = lanes per trajectory: 32 (one trajectory per warp) or 16 (two per warp; used for batches large enough

@@ -161,6 +161,15 @@ struct WarpExec {
     fn(lane, regs);
     __syncwarp(mask);
   }
+  /* A value lane 0 left in the scratch, read by every lane of the group for a uniform branch.  The barrier AFTER the
+   * read keeps a fast lane from overwriting the slot in the next phase before a slow lane has read it (lanes of a warp
+   * are not guaranteed to run in lockstep; compute-sanitizer racecheck flags the pattern without it). */
+  template <typename V>
+  __device__ __forceinline__ V uniform(const V &slot) {
+    const V v = slot;
+    __syncwarp(mask);
+    return v;
+  }
   /* experiment builds only (-DILQR_PHASE_CLOCKS): cycles since the previous tick are charged to phase `id` */
 #if defined(ILQR_PHASE_CLOCKS)
   long long last_clk = 0;
@@ -235,6 +244,8 @@ struct HostExec {
   }
   void stage_wait() {}
   void tick(int) {}
+  template <typename V>
+  V uniform(const V &slot) { return slot; }
 };
 
 /* Accumulates products in index order.  The reference's sums start from zero (Eigen zero-initialises, the
@@ -661,7 +672,7 @@ struct Core {
         }
       });
       ex.tick(3);
-      if (sc.qp.result < 1) return false;
+      if (ex.uniform(sc.qp.result) < 1) return false;
       /* ---- B2: [Vxx | Vx] (:391-392) and the symmetrisation (:393); column n (Vx) is copied:
        * 0.5 * (v + v) == v exactly ---- */
       ex.lanes([&](int lane, Lane &) {
@@ -1014,10 +1025,13 @@ struct Core {
   }
   /* one trip of the loop body; returns whether another one follows */
   ILQR_HD bool iterate_trip() {
-    if (!(sc.st.iter < P.max_iter && trips_left > 0 && sc.st.status == kRunning)) return false;
+    {
+      const int it = ex.uniform(sc.st.iter), status = ex.uniform(sc.st.status);
+      if (!(it < P.max_iter && trips_left > 0 && status == kRunning)) return false;
+    }
     trips_left--;
     /* :115-120 */
-    if (sc.st.flg_change || !have_derivs) {
+    if (ex.uniform(sc.st.flg_change) || !have_derivs) {
       ex.tick(15);
       derivative_sweep();
       have_derivs = true;
@@ -1048,7 +1062,7 @@ struct Core {
         }
       });
       if (diverge != 0) {
-        if (sc.flag) break;
+        if (ex.uniform(sc.flag)) break;
         continue;
       }
       back_done = true;
@@ -1065,7 +1079,7 @@ struct Core {
       }
     });
     ex.tick(9);
-    if (sc.flag == 2) return false; /* gradient exit: `break` before iter++ */
+    if (ex.uniform(sc.flag) == 2) return false; /* gradient exit: `break` before iter++ */
     if (back_done) rollout_candidates();
     ex.tick(10);
     /* the acceptance test :199-213 in the reference's serial order */
@@ -1095,9 +1109,9 @@ struct Core {
       }
       s.alpha = alpha;
     });
-    const bool fwd_done = sc.flag == 1;
+    const bool fwd_done = ex.uniform(sc.flag) == 1;
     ex.tick(11);
-    if (fwd_done) commit_candidate(sc.st.alpha_index);
+    if (fwd_done) commit_candidate(ex.uniform(sc.st.alpha_index));
     ex.tick(12);
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
@@ -1125,7 +1139,7 @@ struct Core {
       if (!sc.flag) s.iter++;
     });
     ex.tick(13);
-    return sc.flag == 0;
+    return ex.uniform(sc.flag) == 0;
   }
   ILQR_HD void op_iterate(int n_iters) {
     iterate_begin(n_iters);

@@ -94,13 +94,21 @@ ILQR_HD void sincos_core(double x, double *sn, double *cs) {
 /* The platform's sincos for arguments outside the range of sincos_core.  Out of line on the device: it is never
  * reached by a sane trajectory, and inlined (several hundred instructions of Payne-Hanek reduction at every call
  * site) it sat between the hot instructions and cost instruction-cache misses (profiles/r1j: 13 % of the stall
- * samples were "no instruction"). */
-#if defined(__CUDACC__) && defined(ILQR_SINCOS_SLOW_NOINLINE)
+ * samples were "no instruction").  Argument and results travel BY VALUE: a noinline callee that is handed the
+ * addresses of the callers' sn[] / cs[] forces those arrays into local memory on the hot path as well (measured: -12 %). */
+struct SinCos {
+  double s, c;
+};
+#if defined(__CUDACC__) && !defined(ILQR_SINCOS_SLOW_INLINE)
 __host__ __device__ __noinline__
 #else
 ILQR_HD
 #endif
-void sincos_slow(double x, double *sn, double *cs) { ::sincos(x, sn, cs); }
+SinCos sincos_slow(double x) {
+  SinCos r;
+  ::sincos(x, &r.s, &r.c);
+  return r;
+}
 
 ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
 #if defined(ILQR_TRIG_LIBM) && !defined(__CUDACC__)
@@ -110,7 +118,9 @@ ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
   return;
 #endif
   if (__builtin_expect(!sincos_in_range(x), 0)) {
-    sincos_slow(x, sn, cs);
+    const SinCos r = sincos_slow(x);
+    *sn = r.s;
+    *cs = r.c;
     return;
   }
   sincos_core(x, sn, cs);
@@ -217,8 +227,14 @@ ILQR_HD void sincos_detN(const double *x, double *sn, double *cs) {
   bool ok = true;
 #pragma unroll
   for (int i = 0; i < K; i++) ok = ok && sincos_in_range(x[i]);
-  if (__builtin_expect(!ok, 0)) {
-    for (int i = 0; i < K; i++) sincos_det(x[i], sn + i, cs + i);
+  if (__builtin_expect(!ok, 0)) { /* the in-range ones already hold what sincos_det would give */
+#pragma unroll
+    for (int i = 0; i < K; i++)
+      if (!sincos_in_range(x[i])) {
+        const SinCos r = sincos_slow(x[i]);
+        sn[i] = r.s;
+        cs[i] = r.c;
+      }
   }
 }
 

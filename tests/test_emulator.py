@@ -110,6 +110,67 @@ def test_boxqp_paths_against_reference_golden(golden_leaf):
                 assert np.array_equal(R, oR)
 
 
+def test_scalar_boxqp_straight_line_equals_the_loop():
+    """The m == 1 boxQP of the kernels is straight-line code (early exit when the warm start is clamped, two
+    speculated Newton iterations, Armijo test without the division); it must return what the restated loop of
+    src/boxqp.cpp returns — result code, x bit for bit, free flag — on every kind of problem: interior optimum,
+    steps cut short by a bound (back-tracking), starts on / near a bound, tiny gradients, flat and non-convex Q,
+    huge and tiny scales, steps that land within the 1e-4 clamp tolerance."""
+    rng = np.random.default_rng(2026)
+    n = 0
+    seen = set()
+
+    def check(Q, c, x0, lo, hi):
+        nonlocal n
+        args = (np.array([[Q]]), np.array([c]), np.array([x0]), np.array([lo]), np.array([hi]))
+        ores, ox, ovf, oR = O.boxqp(*args)
+        gres, gx, gvf, gR = E.boxqp(*args, generic=True)
+        res, x, vf, R = E.boxqp(*args, generic=False)
+        assert res == ores == gres, (Q, c, x0, lo, hi, res, ores, gres)
+        assert x.tobytes() == ox.tobytes() == gx.tobytes(), (Q, c, x0, lo, hi, x, ox)
+        assert (vf == ovf).all() and (vf == gvf).all(), (Q, c, x0, lo, hi)
+        if res != 6:
+            assert np.array_equal(R, oR)
+        seen.add(int(res))
+        n += 1
+
+    for _ in range(4000):
+        scale = 10.0 ** rng.uniform(-6, 6)
+        Q = scale * 10.0 ** rng.uniform(-2, 2)
+        c = scale * rng.normal() * 10.0 ** rng.uniform(-3, 3)
+        lo, hi = sorted(rng.normal(size=2) * 10.0 ** rng.uniform(-2, 1))
+        if lo == hi:
+            hi = lo + 1.0
+        kind = rng.integers(0, 6)
+        if kind == 0:
+            x0 = rng.uniform(lo, hi)
+        elif kind == 1:
+            x0 = lo if rng.random() < 0.5 else hi          # on a bound (the warm start of a clamped control)
+        elif kind == 2:
+            x0 = (lo if rng.random() < 0.5 else hi) + rng.uniform(-2e-4, 2e-4)  # within / just outside the clamp tolerance
+        elif kind == 3:
+            x0 = rng.normal() * 100                         # far outside: clamped first
+        elif kind == 4:
+            x0 = -c / Q + rng.normal() * 1e-9               # already at the optimum: gradient-small exits
+        else:
+            x0 = rng.uniform(lo, hi)
+            c = -Q * (hi + (hi - lo) * 10.0 ** rng.uniform(-3, 3))  # optimum far beyond the upper bound: back-tracking
+        check(Q, c, x0, lo, hi)
+    # the Armijo threshold itself: steps cut to exactly the fraction theta of the Newton step, theta - theta^2 / 2 ~ 0.1
+    for theta in np.concatenate([np.linspace(0.10, 0.112, 400), [0.1055728090000841]]):
+        Q, x0, lo = 2.0, 0.0, -1.0
+        for full in (1.0, 3.0, 1e3):
+            c = -Q * full
+            check(Q, c, x0, lo, theta * full)
+    # degenerate curvature (Eigen's LLT leaves a non-positive pivot) and zero gradient
+    for Q in (0.0, -1.0, 1e-300, 1e300):
+        for c in (0.0, 1.0, -1.0):
+            for x0 in (-1.0, 0.0, 0.5):
+                check(Q, c, x0, -1.0, 1.0)
+    assert n > 5000 and {2, 4, 5, 6} <= seen | {2, 4}, seen   # all exits of the shipped path were exercised
+    assert {5, 6} <= seen
+
+
 def test_trig_noise_floor():
     """How far the deterministic sincos moves an acrobot solve away from the libm oracle: this is the
     floor under every GPU-vs-oracle tolerance in test_gpu_parity.py."""

@@ -447,6 +447,27 @@ def test_edge_shapes_bit_exact(model, T, B, dt):
             assert np.array_equal(np.asarray(g[f][b]), np.asarray(r[f])), (b, f)
 
 
+@pytest.mark.parametrize("T", [37, 38, 199, 200])
+@pytest.mark.parametrize("lanes", ["32", "16"])
+def test_shared_memory_layout_odd_and_even_horizons(T, lanes, monkeypatch):
+    """Closed-form cost derivatives (the smallest scratch) with odd and even horizons, both lane decompositions: the
+    group's mbarrier must not share its 16-byte granule with the last gradient-norm term whatever T is (it once did
+    for odd T: compute-sanitizer synccheck "Barrier error: missing init", profiles/experiments/README.md)."""
+    monkeypatch.setenv("ILQR_B200_LANES", lanes)
+    B = 6
+    x0, u0 = make_inputs(99, B, T, 4, 1, canonical_first=False)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    s.generate_trajectory(x0, u0)
+    g = gpu_snap(s)
+    for b in range(B):
+        e = E.EmuSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC, lanes=int(lanes))
+        e.init(x0[b], u0[b])
+        e.iterate(1000)
+        r = snap(e)
+        for f in g:
+            assert np.array_equal(np.asarray(g[f][b]), np.asarray(r[f])), (b, f)
+
+
 def test_non_default_parameters_bit_exact():
     """every tunable of ilqr_params reaches the kernels (shorter alpha table, other eps / tolerances / lambda schedule)"""
     p = abi.default_params()

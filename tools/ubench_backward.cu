@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128, UB_MINB) k(const __grid_constant__ Args a
   Ex ex;
   ex.lane = threadIdx.x & (UB_G - 1);
   ex.mask = UB_G == 32 ? 0xffffffffu : (0xffffu << ((threadIdx.x & 31) & ~(UB_G - 1)));
-  ex.init_barrier(reinterpret_cast<unsigned long long *>(smem + sizeof(Sc) + a.P.T * 8 + 8));
+  ex.init_barrier(reinterpret_cast<unsigned long long *>(smem + ((sizeof(Sc) + a.P.T * 8 + 15) & ~(size_t)15)));
   CoreT core(a.P, sc, ex, a.tr, sl);
   core.load_state();
   long long t[8];
@@ -90,7 +90,7 @@ int main(int argc, char **argv) {
   a.sl.cand_u = (double *)dev(nullptr, 11 * T * 8);
   a.P.bulk_f = argc > 1 ? atoi(argv[1]) : 1;
   a.out = (long long *)dev(nullptr, 64);
-  const size_t smem = sizeof(Sc) + T * 8 + 32;
+  const size_t smem = ((sizeof(Sc) + T * 8 + 15) & ~(size_t)15) + 16;
   k<<<1, 32, smem>>>(a);
   long long h[8];
   cudaMemcpy(h, a.out, 64, cudaMemcpyDeviceToHost);
