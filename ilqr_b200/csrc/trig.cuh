@@ -93,7 +93,7 @@ ILQR_HD void sincos_core(double x, double *sn, double *cs) {
 
 /* The platform's sincos for arguments outside the range of sincos_core.  Out of line on the device: it is never
  * reached by a sane trajectory, and inlined (several hundred instructions of Payne-Hanek reduction at every call
- * site) it sat between the hot instructions and cost instruction-cache misses (profiles/r1j: 13 % of the stall
+ * site) it sat between the hot instructions and cost instruction-cache misses (ncu, bulk regime: 12-13 % of the stall
  * samples were "no instruction").  Argument and results travel BY VALUE: a noinline callee that is handed the
  * addresses of the callers' sn[] / cs[] forces those arrays into local memory on the hot path as well (measured: -12 %). */
 struct SinCos {
@@ -149,7 +149,7 @@ ILQR_HD void sincos_coreN(const double *x, double *sn, double *cs) {
   const double *tab = kTrigHost;
 #endif
   /* the four reduction constants as immediates: they head the dependency chain, and a constant-memory load there
-   * is exposed latency (profiles/r1k: 3.9 % of the stall samples sat on the first multiply) */
+   * is exposed latency (ncu: 3.9 % of the stall samples sat on the first multiply) */
   const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00, pio2_2 = 6.07710050630396597660e-11,
                pio2_2t = 2.02226624879595063154e-21;
   const double S1 = tab[4], S2 = tab[5], S3 = tab[6], S4 = tab[7], S5 = tab[8], S6 = tab[9];
