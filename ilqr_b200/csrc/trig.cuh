@@ -53,6 +53,30 @@ static const double kTrigHost[16] = ILQR_TRIG_TABLE;
 /* |x| small enough for the two-step Cody-Waite reduction (fdlibm's "medium" range is 2^19 * pi/2) */
 ILQR_HD bool sincos_in_range(double x) { return ::fabs(x) < 8.0e5; } /* false for NaN */
 
+/* v with its sign flipped when `bit` (0 or 2) is 2: -v is exactly a sign flip, and as an integer operation on the high
+ * word it is one logic instruction instead of a negation in the fp64 pipe and two selects */
+ILQR_HD double flip_if2(double v, int bit) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) ^ (bit << 30), __double2loint(v));
+#else
+  unsigned long long b;
+  __builtin_memcpy(&b, &v, 8);
+  b ^= (unsigned long long)(unsigned)(bit & 2) << 62;
+  __builtin_memcpy(&v, &b, 8);
+  return v;
+#endif
+}
+
+ILQR_HD int lo32(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(v);
+#else
+  long long b;
+  __builtin_memcpy(&b, &v, 8);
+  return (int)(unsigned)(b & 0xffffffffLL);
+#endif
+}
+
 /* The branch-free core: exact for sincos_in_range(x), meaningless (but harmless) otherwise.  Callers that
  * need several sincos of independent arguments call this back to back and test the ranges once afterwards,
  * so the evaluations sit in one basic block and the instruction scheduler interleaves their dependency
@@ -87,8 +111,8 @@ ILQR_HD void sincos_core(double x, double *sn, double *cs) {
   /* quadrant */
   const double a = (n & 1) ? kc : ks;
   const double b = (n & 1) ? ks : kc;
-  *sn = (n & 2) ? -a : a;
-  *cs = ((n + 1) & 2) ? -b : b;
+  *sn = flip_if2(a, n & 2);
+  *cs = flip_if2(b, (n + 1) & 2);
 }
 
 /* The platform's sincos for arguments outside the range of sincos_core.  Out of line on the device: it is never
@@ -124,16 +148,6 @@ ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
     return;
   }
   sincos_core(x, sn, cs);
-}
-
-ILQR_HD int lo32(double v) {
-#if defined(__CUDA_ARCH__)
-  return __double2loint(v);
-#else
-  long long b;
-  __builtin_memcpy(&b, &v, 8);
-  return (int)(unsigned)(b & 0xffffffffLL);
-#endif
 }
 
 /* K independent arguments at once: sincos_core written "one operation, K arguments" at a time, so that the
@@ -210,8 +224,8 @@ ILQR_HD void sincos_coreN(const double *x, double *sn, double *cs) {
   ILQR_EACH {
     const double a = (n[i] & 1) ? kc[i] : ks[i];
     const double b = (n[i] & 1) ? ks[i] : kc[i];
-    sn[i] = (n[i] & 2) ? -a : a;
-    cs[i] = ((n[i] + 1) & 2) ? -b : b;
+    sn[i] = flip_if2(a, n[i] & 2);
+    cs[i] = flip_if2(b, (n[i] + 1) & 2);
   }
 #undef ILQR_EACH
 }
