@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("ILQR_B200_LIB") or os.path.join(ROOT, "ilqr_b200", "l
 
 MAX_N, MAX_M, MAX_ALPHA = 8, 4, 16
 MODEL_ACROBOT, MODEL_DOUBLE_INTEGRATOR = 0, 1
+MODEL_USER_BASE = 100  # ids of models registered at run time (register_model)
 F64, F32 = 0, 1
 COST_FD, COST_ANALYTIC = 0, 1
 RUNNING, EXIT_GRAD, EXIT_TOLFUN, EXIT_LAMBDA_MAX, EXIT_MAXITER = 0, 1, 2, 3, 4
@@ -98,7 +99,7 @@ EXPORTS = [
     "ilqr_default_params", "ilqr_model_info", "ilqr_create", "ilqr_destroy", "ilqr_last_error",
     "ilqr_set_initial", "ilqr_warm_start", "ilqr_iterate", "ilqr_solve", "ilqr_backward_once",
     "ilqr_rollout_once", "ilqr_get", "ilqr_sync", "ilqr_stream", "ilqr_launch_count", "ilqr_make_inputs",
-    "ilqr_version",
+    "ilqr_version", "ilqr_register_model", "ilqr_compile_model",
 ]
 
 
@@ -134,5 +135,36 @@ def load():
     L.ilqr_make_inputs.argtypes = [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
                                    C.c_int, dp, dp]
     L.ilqr_version.restype = C.c_char_p
+    L.ilqr_register_model.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, dp, dp, ip]
+    L.ilqr_compile_model.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t]
     _lib = L
     return L
+
+
+def model_dims(model):
+    """(n, m) of a built-in or registered model."""
+    if model in MODEL_DIMS:
+        return MODEL_DIMS[model]
+    n, m = C.c_int32(), C.c_int32()
+    if load().ilqr_model_info(model, C.byref(n), C.byref(m), None, None) != 0:
+        raise ValueError("unknown model id %r" % (model,))
+    return n.value, m.value
+
+
+def register_model(struct_name, cuda_source, n, m, u_min, u_max):
+    """A user model as CUDA source (the device twin of a `Model` subclass, include/ilqr_b200.h: ilqr_register_model).
+    Returns the model id for BatchILQR(model=...).  Compiled by NVRTC when a handle of it first launches."""
+    lo = (C.c_double * MAX_M)(*[float(v) for v in u_min])
+    hi = (C.c_double * MAX_M)(*[float(v) for v in u_max])
+    mid = C.c_int32()
+    rc = load().ilqr_register_model(struct_name.encode(), cuda_source.encode(), int(n), int(m), lo, hi, C.byref(mid))
+    if rc != 0:
+        raise ValueError("ilqr_register_model failed (%d): %s" % (rc, (load().ilqr_last_error(None) or b"?").decode()))
+    return mid.value
+
+
+def compile_model(model, dtype=F64, cost_deriv=COST_ANALYTIC):
+    """NVRTC-compile a registered model now (no GPU needed); returns (rc, compiler log)."""
+    log = C.create_string_buffer(1 << 16)
+    rc = load().ilqr_compile_model(int(model), int(dtype), int(cost_deriv), log, len(log))
+    return rc, log.value.decode(errors="replace")

@@ -39,8 +39,12 @@ inline void default_params(ilqr_params *p) {
   p->fd_eps = 1e-3;
 }
 
+/* models registered at run time (ilqr_register_model, ilqr_b200.cu) answer through this hook */
+inline int (*g_user_model_info)(int model_id, int *n, int *m, double *u_min, double *u_max) = nullptr;
+
 /* n, m and the model's own limits (Model::x_dims/u_dims/u_min/u_max) */
 inline int model_info(int model_id, int *n, int *m, double *u_min, double *u_max) {
+  if (model_id >= ILQR_MODEL_USER_BASE) return g_user_model_info ? g_user_model_info(model_id, n, m, u_min, u_max) : -1;
   if (model_id == ILQR_MODEL_ACROBOT) { /* include/acrobot.h:27-28,37 */
     *n = Acrobot::N;
     *m = Acrobot::M;
@@ -90,6 +94,8 @@ inline int make_solve_params(const ilqr_desc &d, SolveParams<S> *out) {
   }
   if (d.model_id == ILQR_MODEL_ACROBOT) {
     P.mp[0] = S(3.1415); /* include/acrobot.h:20-21: the literal, not pi */
+  } else if (d.model_id >= ILQR_MODEL_USER_BASE) {
+    for (int i = 0; i < 16; i++) P.mp[i] = S(d.model_params[i]);
   } else {
     for (int i = 0; i < 4; i++) P.mp[i] = S(d.model_params[i]);
   }

@@ -21,6 +21,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <typeinfo>
 #include <vector>
 
 #include "common.h"
@@ -50,6 +51,20 @@ class iLQR {
   double get_cost() const { return cost_s; }
   int get_iterations() const { return iterations; }
   int get_status() const { return status; } /* ILQR_EXIT_* of include/ilqr_b200.h */
+
+  /* A Model subclass of the user's own.  The host object (dynamics / cost / final_cost virtuals, include/model.h:6-21)
+   * cannot run in a kernel, so its device twin is registered once as CUDA source — a struct with the static interface
+   * of ilqr_b200/csrc/models.cuh, see include/ilqr_b200.h: ilqr_register_model — and `new iLQR(new MyModel, dt)` then
+   * finds it by the dynamic type of the object.  model_params reach the twin's functions as `mp`.  The solver checks
+   * the twin against the host virtuals at construction: one Euler step and both costs on a few probe points through
+   * the GPU must agree with p_dyn->integrate_dynamics / cost / final_cost to 1e-9. */
+  template <class UserModel>
+  static void register_device_twin(const char *struct_name, const char *cuda_source,
+                                   const std::vector<double> &model_params = std::vector<double>()) {
+    register_device_twin(typeid(UserModel), struct_name, cuda_source, model_params);
+  }
+  static void register_device_twin(const std::type_info &type, const char *struct_name, const char *cuda_source,
+                                   const std::vector<double> &model_params);
 
   /* B independent problems at once: X0 is B x n, U0[b] the T initial controls of problem b.
    * Returns the final costs; the trajectory of problem b is then available through batch_xs(b) etc. */

@@ -21,6 +21,9 @@
 #include "../csrc/models.cuh"  // host instantiation of the device twins, for the construction-time check
 #include "ilqr.h"
 
+#include <map>
+#include <typeindex>
+
 namespace {
 
 void check(int rc, ilqr_handle *h, const char *what) {
@@ -47,6 +50,57 @@ void verify_twin(Model &m, const double *mp, double dt) {
   }
 }
 
+struct UserTwin {
+  int model_id = -1;
+  std::vector<double> params;
+  std::string pending_name, pending_source;
+};
+std::map<std::type_index, UserTwin> &user_twins() {
+  static std::map<std::type_index, UserTwin> m;
+  return m;
+}
+
+/* the device twin of a user model against the host object, through the GPU: one open-loop Euler step and the costs
+ * (ilqr_set_initial = iLQR::init_traj on a horizon of one) on a few probe points */
+void verify_user_twin(Model &m, int model_id, const double *mp, double dt) {
+  const int n = m.x_dims, mu = m.u_dims, B = 4;
+  ilqr_desc d;
+  memset(&d, 0, sizeof(d));
+  d.model_id = model_id;
+  d.dtype = ILQR_F64;
+  d.cost_deriv = ILQR_COST_FD;
+  d.T = 1;
+  d.B = B;
+  d.dt = dt;
+  for (int i = 0; i < 16; i++) d.model_params[i] = mp[i];
+  ilqr_default_params(&d.params);
+  ilqr_handle *h = nullptr;
+  if (ilqr_create(&d, &h) != ILQR_OK) throw std::runtime_error(std::string("iLQR: ") + ilqr_last_error(nullptr));
+  std::vector<double> x0((size_t)B * n), u0((size_t)B * mu), xs((size_t)B * 2 * n), cost(B);
+  for (int b = 0; b < B; b++) {
+    for (int i = 0; i < n; i++) x0[(size_t)b * n + i] = 0.3 * std::sin(1.0 + 2.1 * b + 0.7 * i);
+    for (int j = 0; j < mu; j++) u0[(size_t)b * mu + j] = 0.2 * std::cos(0.5 + 1.3 * b + j);
+  }
+  int rc = ilqr_set_initial(h, x0.data(), u0.data(), 0);
+  if (rc == ILQR_OK) rc = ilqr_get(h, ILQR_F_XS, xs.data(), 0);
+  if (rc == ILQR_OK) rc = ilqr_get(h, ILQR_F_COST, cost.data(), 0);
+  const std::string err = rc == ILQR_OK ? "" : ilqr_last_error(h);
+  ilqr_destroy(h);
+  if (rc != ILQR_OK) throw std::runtime_error("iLQR: the device twin did not run: " + err);
+  double worst = 0;
+  for (int b = 0; b < B; b++) {
+    VectorXd x(n), u(mu);
+    for (int i = 0; i < n; i++) x(i) = x0[(size_t)b * n + i];
+    for (int j = 0; j < mu; j++) u(j) = u0[(size_t)b * mu + j];
+    const VectorXd x1 = m.integrate_dynamics(x, u, dt);
+    for (int i = 0; i < n; i++) worst = std::max(worst, std::fabs(x1(i) - xs[((size_t)b * 2 + 1) * n + i]));
+    const double c = m.cost(x, u) + m.final_cost(x1);
+    worst = std::max(worst, std::fabs(c - cost[b]) / (1 + std::fabs(c)));
+  }
+  if (!(worst < 1e-9))
+    throw std::runtime_error("iLQR: the registered device twin disagrees with the host Model object (max error " + std::to_string(worst) + ")");
+}
+
 }  // namespace
 
 iLQR::iLQR(Model *p_dyn, double timeDelta) : dt(timeDelta) {
@@ -60,9 +114,35 @@ iLQR::iLQR(Model *p_dyn, double timeDelta) : dt(timeDelta) {
     for (int i = 0; i < 4; i++) model_params[i] = d->goal(i);
     verify_twin<ilqr::DoubleIntegrator>(*p_dyn, model_params, dt);
   } else {
-    throw std::runtime_error(std::string("iLQR: no device twin for Model subclass ") + typeid(*p_dyn).name() +
-                             " (ilqr_b200/csrc/models.cuh); there is no CPU fallback");
+    const auto it = user_twins().find(std::type_index(typeid(*p_dyn)));
+    if (it == user_twins().end())
+      throw std::runtime_error(std::string("iLQR: no device twin for Model subclass ") + typeid(*p_dyn).name() +
+                               " (built in: ilqr_b200/csrc/models.cuh; your own: iLQR::register_device_twin); there is no CPU fallback");
+    if (it->second.model_id < 0) { /* first object of this type: n, m and the limits are the object's (model.h:17-20) */
+      double lo[ILQR_MAX_M] = {0}, hi[ILQR_MAX_M] = {0};
+      for (int j = 0; j < p_dyn->u_dims && j < ILQR_MAX_M; j++) {
+        lo[j] = p_dyn->u_min(j);
+        hi[j] = p_dyn->u_max(j);
+      }
+      int32_t id = -1;
+      if (ilqr_register_model(it->second.pending_name.c_str(), it->second.pending_source.c_str(), p_dyn->x_dims, p_dyn->u_dims,
+                              lo, hi, &id) != ILQR_OK)
+        throw std::runtime_error(std::string("iLQR: ") + ilqr_last_error(nullptr));
+      it->second.model_id = id;
+    }
+    model_id = it->second.model_id;
+    for (size_t i = 0; i < it->second.params.size() && i < 16; i++) model_params[i] = it->second.params[i];
+    verify_user_twin(*p_dyn, model_id, model_params, dt);
   }
+}
+
+void iLQR::register_device_twin(const std::type_info &type, const char *struct_name, const char *cuda_source,
+                                const std::vector<double> &params) {
+  UserTwin t;
+  t.params = params;
+  t.pending_name = struct_name;
+  t.pending_source = cuda_source;
+  user_twins()[std::type_index(type)] = t; /* n, m and the limits are the object's: registration with the library happens at first construction */
 }
 
 iLQR::~iLQR() { ilqr_destroy(h); }

@@ -26,6 +26,7 @@
 #ifndef ILQR_B200_H_
 #define ILQR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -39,6 +40,7 @@ extern "C" {
 /* model_id: device twins of the reference's Model subclasses */
 #define ILQR_MODEL_ACROBOT 0            /* include/acrobot.h            n=4 m=1 */
 #define ILQR_MODEL_DOUBLE_INTEGRATOR 1  /* include/double_integrator.h  n=4 m=2, model_params[0..3] = goal */
+#define ILQR_MODEL_USER_BASE 100        /* ids >= 100: models registered at run time, ilqr_register_model() */
 
 #define ILQR_F64 0
 #define ILQR_F32 1
@@ -126,6 +128,19 @@ typedef struct ilqr_handle ilqr_handle;
 int ilqr_default_params(ilqr_params *p);
 /* n, m, default limits of a model twin (Model::x_dims/u_dims/u_min/u_max, include/model.h:17-20) */
 int ilqr_model_info(int32_t model_id, int32_t *n, int32_t *m, double *u_min, double *u_max);
+
+/* The plugin surface on the GPU side (include/model.h:6-21: a user writes dynamics / cost / final_cost and hands
+ * the Model to the solver).  A host vtable cannot run in a kernel, so a user model is its device twin as CUDA source:
+ * a struct `struct_name` with the static interface of ilqr_b200/csrc/models.cuh — N, M, dynamics, cost, final_cost,
+ * cost_d1, cost_d2 (closed-form cost derivatives; may return 0 if only ILQR_COST_FD is used), kConfigVars, Config,
+ * configure, dynamics_cfg — templated on the scalar type and marked ILQR_HD.  The library compiles its own solver
+ * kernel around that struct with NVRTC (sm_100a, no FMA contraction) the first time a handle of that model
+ * launches; ilqr_desc.model_params[0..15] reach the struct's functions as `mp`.  u_min / u_max [m] are the model's
+ * own limits (Model::u_min/u_max).  Returns the id to put in ilqr_desc.model_id (>= ILQR_MODEL_USER_BASE). */
+int ilqr_register_model(const char *struct_name, const char *cuda_source, int32_t n, int32_t m, const double *u_min,
+                        const double *u_max, int32_t *model_id);
+/* Compile a registered model now (NVRTC only: needs no GPU) and report the compiler's log; 0 = it compiles. */
+int ilqr_compile_model(int32_t model_id, int32_t dtype, int32_t cost_deriv, char *log, size_t log_bytes);
 
 /* `new iLQR(model, dt)` for B instances (include/ilqr.h:30-44). */
 int ilqr_create(const ilqr_desc *desc, ilqr_handle **out);
