@@ -1023,11 +1023,15 @@ struct Core {
     });
     store_state();
   }
-  /* one trip of the loop body; returns whether another one follows */
-  ILQR_HD bool iterate_trip() {
+  /* One trip of the loop body, in three parts so that a warp carrying two trajectories can run the line searches of
+   * both at once (ilqr_kernel.cuh):  trip_pre — derivatives and backward pass, up to the gradient test;
+   * rollout_candidates — the line search's rollouts, only after kTripRoll;  trip_post — acceptance, commit, lambda
+   * schedule, returns whether another trip follows.  iterate_trip() is the three in sequence. */
+  enum { kTripStop = 0, kTripRoll = 1, kTripNoRoll = 2 };
+  ILQR_HD int trip_pre() {
     {
       const int it = ex.uniform(sc.st.iter), status = ex.uniform(sc.st.status);
-      if (!(it < P.max_iter && trips_left > 0 && status == kRunning)) return false;
+      if (!(it < P.max_iter && trips_left > 0 && status == kRunning)) return kTripStop;
     }
     trips_left--;
     /* :115-120 */
@@ -1079,9 +1083,11 @@ struct Core {
       }
     });
     ex.tick(9);
-    if (ex.uniform(sc.flag) == 2) return false; /* gradient exit: `break` before iter++ */
-    if (back_done) rollout_candidates();
-    ex.tick(10);
+    if (ex.uniform(sc.flag) == 2) return kTripStop; /* gradient exit: `break` before iter++ */
+    return back_done ? kTripRoll : kTripNoRoll;
+  }
+  ILQR_HD bool trip_post(int pre) {
+    const bool back_done = pre == kTripRoll;
     /* the acceptance test :199-213 in the reference's serial order */
     ex.lanes([&](int lane, Lane &) {
       if (lane != 0) return;
@@ -1140,6 +1146,13 @@ struct Core {
     });
     ex.tick(13);
     return ex.uniform(sc.flag) == 0;
+  }
+  ILQR_HD bool iterate_trip() {
+    const int pre = trip_pre();
+    if (pre == kTripStop) return false;
+    if (pre == kTripRoll) rollout_candidates();
+    ex.tick(10);
+    return trip_post(pre);
   }
   ILQR_HD void op_iterate(int n_iters) {
     iterate_begin(n_iters);

@@ -38,6 +38,6 @@ for B in Bs:
             s.sync()
             best = min(best, time.perf_counter() - t0)
         it = s.get("iters")
-        print("B=%d lanes=%d  solve %.3f ms  trips %d (mean %.1f max %d)  %.3f Mtrips/s  %.1f us/trip-of-longest" % (
-            B, ln, best * 1e3, it.sum(), it.mean(), it.max(), it.sum() / best / 1e6, best * 1e6 / it.max()), flush=True)
+        print("B=%d lanes=%d  solve %.3f ms  trips %d (mean %.1f max %d)  %.3f Mtrips/s  %.1f us/trip-of-longest  cost checksum %.12e" % (
+            B, ln, best * 1e3, it.sum(), it.mean(), it.max(), it.sum() / best / 1e6, best * 1e6 / it.max(), s.get("cost").sum()), flush=True)
         s.close()
