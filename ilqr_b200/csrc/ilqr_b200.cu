@@ -155,6 +155,11 @@ int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
   }
   a.P.bulk_f = ((size_t)h->slotF % 16 == 0) && (((size_t)h->desc.T * (N + M) * N * sizeof(S)) % 16 == 0) &&
                (((size_t)kTileB * (N + M) * N * sizeof(S)) % 16 == 0);
+  {
+    constexpr size_t ncf = Scratch<N, M, S, CD>::NCF;
+    a.P.bulk_c = CD == kCostFD && ((size_t)h->slotC % 16 == 0) && (((size_t)h->desc.T * ncf * sizeof(S)) % 16 == 0) &&
+                 (((size_t)kTileB * ncf * sizeof(S)) % 16 == 0);
+  }
   a.slotF = (S *)h->slotF;
   a.slotC = (S *)h->slotC;
   a.slotCandX = (S *)h->slotCandX;

@@ -70,6 +70,7 @@ struct SolveParams {
   S mp[16];
   QPParams<S> qp;
   int bulk_f; /* host-set: every tile of the per-warp Jacobian buffer starts 16-byte aligned (bulk copy allowed) */
+  int bulk_c; /* the same for the per-warp buffer of finite-difference cost derivatives */
 };
 
 /* per-trajectory solver state that survives between launches (one slot per trajectory) */
@@ -111,7 +112,7 @@ struct Scratch {
   /* staged tiles: rollouts use kTile timesteps, the backward pass the first kTileB of the same arrays */
   S xs[kTile * N], us[kTile * M], K[kTile * M * N], k[kTile * M];
   alignas(16) S Ft[kTileB * NM * N];         /* backward: Jacobian columns of the tile (bulk-copy target) */
-  S Ct[CD == kCostFD ? kTileB * NCF : 1];    /* backward: FD cost derivatives of the tile (full layout) */
+  alignas(16) S Ct[CD == kCostFD ? kTileB * NCF : 1]; /* backward: FD cost derivatives of the tile (full layout; bulk-copy target) */
   /* one timestep */
   S x[N], u[M];         /* xs[T] and a zero control for the terminal derivatives */
   S Cf[NCF];            /* terminal cost derivatives, full layout */
@@ -198,12 +199,15 @@ struct WarpExec {
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp(mask);
   }
+  /* Any number of stage_issue calls, then one stage_wait: every copy announces its bytes on the group's mbarrier
+   * (expect_tx) before it is issued, and the group's single arrival is made in stage_wait, so the barrier phase
+   * completes exactly when all of them have landed. */
   __device__ __forceinline__ void stage_issue(S *dst, const S *src, int count, bool aligned) {
     const unsigned bytes = (unsigned)count * (unsigned)sizeof(S);
     if (aligned && (bytes & 15u) == 0) {
       if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* earlier generic reads of the destination */
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        if (!(phase & 2u)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* earlier generic reads of the destinations */
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
                      "l"(src), "r"(bytes), "r"(bar)
                      : "memory");
@@ -215,6 +219,7 @@ struct WarpExec {
   }
   __device__ __forceinline__ void stage_wait() {
     if (phase & 2u) {
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
       unsigned done = 0;
       while (!done) {
         asm volatile(
@@ -727,12 +732,10 @@ struct Core {
       const int t0 = ti * kTileB;
       const int cnt = (T - t0 < kTileB) ? T - t0 : kTileB;
       ex.stage_issue(sc.Ft, sl.F + (size_t)t0 * NM * N, cnt * NM * N, P.bulk_f != 0);
+      if constexpr (CD == kCostFD) ex.stage_issue(sc.Ct, sl.C + (size_t)t0 * NCF, cnt * NCF, P.bulk_c != 0);
       ex.lanes([&](int lane, Lane &) {
         for (int e = lane; e < cnt * N; e += G) sc.xs[e] = tr.xs[t0 * N + e];
         for (int e = lane; e < cnt * M; e += G) sc.us[e] = tr.us[t0 * M + e];
-        if constexpr (CD == kCostFD) {
-          for (int e = lane; e < cnt * NCF; e += G) sc.Ct[e] = ld_fresh(sl.C + (size_t)t0 * NCF + e);
-        }
       });
       ex.stage_wait();
       ex.tick(6);
