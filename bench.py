@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — batched iLQR iterations/sec (acrobot, T=200) on N B200s, next to the CPU reference.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--config cfg2|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--config cfg2|cfg3|cfg4|cfg5]
 
 One STEP = one pass of the hot path over one batch of synthetic instances (SURVEY.md §8d,
 include/ilqr_synth.h, seed 12345): every instance is initialised (`iLQR::init_traj`) and solved to
@@ -46,6 +46,9 @@ CONFIGS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on
     "cfg2": dict(workload="acrobot batch=4096 T=200 fp64, analytic cost derivatives, FD fx/fu (BASELINE configs[1])",
                  B=4096, T=200, cost_deriv="analytic", limits=None),
+    # configs[2]: f32, longer horizon, finite-difference fx/fu, closed-form cost derivatives
+    "cfg3": dict(workload="acrobot batch=65536 T=500 fp32, finite-difference fx/fu, analytic cost derivatives (BASELINE configs[2])",
+                 B=65536, T=500, cost_deriv="analytic", limits=None, dtype="f32"),
     # configs[3]: control-limited, full finite differences
     "cfg4": dict(workload="control-limited acrobot (+-1.5) batch=8192 T=200 fp64, full finite differences (BASELINE configs[3])",
                  B=8192, T=200, cost_deriv="fd", limits=1.5),
@@ -250,15 +253,17 @@ def ours_arm(args, cfg):
     kw = dict(u_min=[-cfg["limits"]], u_max=[cfg["limits"]]) if cfg["limits"] else {}
     from ilqr_b200 import shard
     x0, u0 = synth_inputs(B, T, shard.rank_seed(SEED, rank))  # every rank owns different instances
-    solver = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cd, device=local, **kw)
+    f32 = cfg.get("dtype") == "f32"
+    sbytes, np_t, th_t = (4, np.float32, torch.float32) if f32 else (8, np.float64, torch.float64)
+    solver = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cd, device=local, dtype=abi.F32 if f32 else abi.F64, **kw)
     stream = torch.cuda.ExternalStream(solver.stream, device=dev)
 
-    x0_h = torch.from_numpy(x0).pin_memory()
-    u0_h = torch.from_numpy(u0).pin_memory()
-    cost_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    x0_h = torch.from_numpy(x0.astype(np_t)).pin_memory()  # the handle's dtype: set / get are plain copies
+    u0_h = torch.from_numpy(u0.astype(np_t)).pin_memory()
+    cost_h = torch.empty(B, dtype=th_t).pin_memory()
     iters_h = torch.empty(B, dtype=torch.int32).pin_memory()
     x0_d, u0_d = x0_h.to(dev), u0_h.to(dev)
-    cost_d = torch.empty(B, dtype=torch.float64, device=dev)
+    cost_d = torch.empty(B, dtype=th_t, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
 
@@ -365,7 +370,7 @@ def ours_arm(args, cfg):
     if rank == 0:
         value = cnt[0] / (t_res[0] * 1e-3)
         e2e = cnt[1] / (t_res[1] * 1e-3)
-        b_acc, b_rej = bytes_per_trip(n, m, T, 8)
+        b_acc, b_rej = bytes_per_trip(n, m, T, sbytes)
         alg_bytes_per_launch = (cnt[2] * b_acc + cnt[3] * b_rej) / world / args.steps  # per GPU per solve launch
         solve_s = t_res[2] * 1e-3 / args.steps
         achieved = alg_bytes_per_launch / solve_s / 1e9
@@ -383,7 +388,7 @@ def ours_arm(args, cfg):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_res[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32" if f32 else "f64", "data": "synthetic",
             "config": {"workload": cfg["workload"], "batch_per_gpu": B, "T": T, "seed": SEED,
                        "step": "init_traj + generate_trajectory to termination for every instance; one NCCL gather of final costs when N>1",
                        "l2": "512 MiB buffer written between timed steps (L2 flush)",
@@ -392,21 +397,21 @@ def ours_arm(args, cfg):
                        "fixed_n_mode": {"trips_per_instance": N_FIXED, "value": cnt[4] / (t_res[3] * 1e-3), "unit": UNIT,
                                         "note": "every instance runs exactly N trips in one launch: the kernel's rate without the ragged-termination tail"}},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": t_res[1] / args.steps,
-                    "h2d_bytes_per_step": int(world * (x0_h.numel() + u0_h.numel()) * 8),
-                    "d2h_bytes_per_step": int(world * (B * 8 + B * 4))},
+                    "h2d_bytes_per_step": int(world * (x0_h.numel() + u0_h.numel()) * sbytes),
+                    "d2h_bytes_per_step": int(world * (B * sbytes + B * 4))},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "ilqr_warp_kernel<Acrobot,double,%s> (op_iterate)" % cfg["cost_deriv"],
+            "roofline": {"bound": "hbm", "kernel": "ilqr_warp_kernel<Acrobot,%s,%s> (op_iterate)" % ("float" if f32 else "double", cfg["cost_deriv"]),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel_ms": solve_s * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                         "note": "fp64 finite-difference + boxQP arithmetic bounds this kernel (SURVEY.md §8d secondary ceiling), not HBM"},
+                         "note": "finite-difference + boxQP arithmetic (dependent chains in the %s pipe) bounds this kernel (SURVEY.md §8d secondary ceiling), not HBM" % ("fp32" if f32 else "fp64")},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             n_sample = min(B, cores * args.cpu_per_core)
             kind, it, wall, cpu_cost, used = run_cpu_sample(cfg, x0, u0, n_sample, cores)
-            gcost = cost_h.numpy()[:n_sample]
+            gcost = cost_h.numpy()[:n_sample].astype(np.float64)
             rel = np.abs(gcost - cpu_cost) / np.maximum(np.abs(cpu_cost), 1e-300)
             line["cpu_baseline"] = {"value": it / wall, "unit": UNIT, "cores": used, "kind": kind,
                                     "sample": "first %d of %d instances, solved to termination, %d forked workers, %.1f s wall"
@@ -430,10 +435,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override instances per GPU")
-    ap.add_argument("--cpu-per-core", type=int, default=128, help="CPU baseline: instances per host core in the sample")
+    ap.add_argument("--cpu-per-core", type=int, default=0,
+                    help="CPU baseline: instances per host core in the sample (default: 128 at T=200, scaled down with the horizon)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    if args.cpu_per_core <= 0:  # ~7 s of reference work per core at T = 200; the reference's cost per iteration grows with T
+        args.cpu_per_core = max(4, int(128 * (200.0 / cfg["T"]) ** 2))
     if args.impl == "reference":
         reference_arm(args, cfg)
     else:
