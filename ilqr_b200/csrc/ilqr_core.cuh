@@ -830,11 +830,32 @@ struct Core {
 
   ILQR_HD void load_forward_tile(int t0, int cnt, int mode) {
     ex.lanes([&](int lane, Lane &) {
-      for (int e = lane; e < cnt * N; e += G) sc.xs[e] = tr.xs[t0 * N + e];
-      for (int e = lane; e < cnt * M; e += G) sc.us[e] = tr.us[t0 * M + e];
+      /* all of the tile's loads in flight before the first store to the scratch */
+      constexpr int U = (kTile * N + G - 1) / G, UK = (kTile * M * N + G - 1) / G, U1 = (kTile * M + G - 1) / G;
+      S vx[U], vu[U1], vK[UK], vk[U1];
+#pragma unroll
+      for (int u = 0; u < U; u++) vx[u] = (lane + u * G < cnt * N) ? tr.xs[t0 * N + lane + u * G] : S(0);
+#pragma unroll
+      for (int u = 0; u < U1; u++) vu[u] = (lane + u * G < cnt * M) ? tr.us[t0 * M + lane + u * G] : S(0);
       if (mode != kRollOpen) {
-        for (int e = lane; e < cnt * M * N; e += G) sc.K[e] = tr.K[t0 * M * N + e];
-        for (int e = lane; e < cnt * M; e += G) sc.k[e] = tr.k[t0 * M + e];
+#pragma unroll
+        for (int u = 0; u < UK; u++) vK[u] = (lane + u * G < cnt * M * N) ? tr.K[t0 * M * N + lane + u * G] : S(0);
+#pragma unroll
+        for (int u = 0; u < U1; u++) vk[u] = (lane + u * G < cnt * M) ? tr.k[t0 * M + lane + u * G] : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (lane + u * G < cnt * N) sc.xs[lane + u * G] = vx[u];
+#pragma unroll
+      for (int u = 0; u < U1; u++)
+        if (lane + u * G < cnt * M) sc.us[lane + u * G] = vu[u];
+      if (mode != kRollOpen) {
+#pragma unroll
+        for (int u = 0; u < UK; u++)
+          if (lane + u * G < cnt * M * N) sc.K[lane + u * G] = vK[u];
+#pragma unroll
+        for (int u = 0; u < U1; u++)
+          if (lane + u * G < cnt * M) sc.k[lane + u * G] = vk[u];
       }
     });
   }
@@ -886,11 +907,24 @@ struct Core {
   ILQR_HD void commit_candidate(int a) {
     const int T = P.T;
     ex.lanes([&](int lane, Lane &) {
-      const S *cx = sl.cand_x + (size_t)a * T * N;
-      const S *cu = sl.cand_u + (size_t)a * T * M;
-      for (int e = lane; e < T * N; e += G) tr.xs[N + e] = ld_fresh(cx + e);
-      for (int e = lane; e < T * M; e += G) tr.us[e] = ld_fresh(cu + e);
+      copy_lanes<8>(tr.xs + N, sl.cand_x + (size_t)a * T * N, T * N, lane);
+      copy_lanes<8>(tr.us, sl.cand_u + (size_t)a * T * M, T * M, lane);
     });
+  }
+  /* dst[e] = src[e] for this lane's share e = lane, lane + G, ... with U loads in flight at a time.  Written out
+   * because a plain loop cannot be pipelined by the compiler (dst might alias src, so every load waits for the store
+   * before it): the commit of a 200-step trajectory took 25 full L2 round trips, 10 k cycles. */
+  template <int U>
+  ILQR_HD static void copy_lanes(S *dst, const S *src, int count, int lane) {
+    int e = lane;
+    for (; e + (U - 1) * G < count; e += U * G) {
+      S v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = ld_fresh(src + e + u * G);
+#pragma unroll
+      for (int u = 0; u < U; u++) dst[e + u * G] = v[u];
+    }
+    for (; e < count; e += G) dst[e] = ld_fresh(src + e);
   }
 
   /* One rollout on lane 0 that rewrites xs, us in place (init_traj, warm start, test hook); the
