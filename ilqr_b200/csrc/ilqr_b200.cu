@@ -13,6 +13,10 @@
  *     x0 [B][n]   xs [B][T+1][n]   us [B][T][m]   K [B][T][m][n]   k [B][T][m]
  *     Vx0 [B][n]  Vxx0 [B][n][n]   st [B] (TrajState: cost, lambda, dlambda, dV, counters ...)
  *
+ * The kernels of the built-in models are compiled in translation units of their own (ilqr_model_*.cu through
+ * ilqr_launch.cuh); this file holds the C ABI, the run-time compiled user-model path (ilqr_rtc.inc) and everything
+ * that does not depend on a model.
+ *
  * There is no CPU path in this library: every entry point that computes launches a kernel.
  */
 #include <cuda_runtime.h>
@@ -25,8 +29,8 @@
 #include <string>
 #include <type_traits>
 
-#include "../../include/ilqr_b200.h"
 #include "../../include/ilqr_synth.h"
+#include "ilqr_host.h"
 #include "ilqr_kernel.cuh"
 #include "params.h"
 
@@ -63,22 +67,11 @@ thread_local std::string g_create_error;
 
 }  // namespace
 
-struct ilqr_handle {
-  ilqr_desc desc;
-  int n = 0, m = 0;
-  size_t ssize = 8;
-  cudaStream_t stream = nullptr;
-  void *x0 = nullptr, *xs = nullptr, *us = nullptr, *K = nullptr, *k = nullptr, *Vx0 = nullptr, *Vxx0 = nullptr,
-       *st = nullptr, *tmp = nullptr;
-  void *slotF = nullptr, *slotC = nullptr, *slotCandX = nullptr, *slotCandU = nullptr; /* per resident warp */
-  long long slots = 0;
-  int lanes = 0; /* 0: choose by batch size; 16 / 32: forced (environment ILQR_B200_LANES, for experiments and tests) */
-  unsigned long long *queue = nullptr;
-  int num_sms = 0;
-  int64_t launches = 0;
-  bool initialised = false;
-  std::string err;
-};
+int ilqr_fail(ilqr_handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
 
 namespace {
 
@@ -95,111 +88,17 @@ struct DeviceGuard {
   }
 };
 
-int fail(ilqr_handle *h, int code, const std::string &msg) {
-  if (h) h->err = msg;
-  else g_create_error = msg;
-  return code;
-}
-#define CU(h, call)                                                                                     \
-  do {                                                                                                  \
-    cudaError_t e_ = (call);                                                                            \
-    if (e_ != cudaSuccess)                                                                              \
-      return fail(h, ILQR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
-  } while (0)
+int fail(ilqr_handle *h, int code, const std::string &msg) { return ilqr_fail(h, code, msg); }
 
 }  // namespace
 #include "ilqr_rtc.inc"
 namespace {
 
-template <class Model, typename S, int CD, int G>
-int launch_t(ilqr_handle *h, int op, int n_iters, double scalar) {
-  constexpr int N = Model::N, M = Model::M;
-  constexpr int kGroupsPerCta = kThreads / G;
-  KArgs<S> a;
-  if (make_solve_params<S>(h->desc, &a.P) != 0) return fail(h, ILQR_E_INVALID, "bad parameters");
-  a.x0 = (const S *)h->x0;
-  a.xs = (S *)h->xs;
-  a.us = (S *)h->us;
-  a.K = (S *)h->K;
-  a.k = (S *)h->k;
-  a.Vx0 = (S *)h->Vx0;
-  a.Vxx0 = (S *)h->Vxx0;
-  a.st = (TrajState<S> *)h->st;
-  a.queue = h->queue;
-  a.B = h->desc.B;
-  a.op = op;
-  a.n_iters = n_iters;
-  a.scalar = S(scalar);
-  auto kern = ilqr_warp_kernel<Model, S, CD, G>;
-  const size_t smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S, G>>::Sc, S>(h->desc.T) * kGroupsPerCta;
-  if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-  if (per_sm < 1) return fail(h, ILQR_E_CUDA, "kernel does not fit on an SM");
-  long long want = (h->desc.B + kGroupsPerCta - 1) / kGroupsPerCta;
-  long long cap = (long long)per_sm * h->num_sms;
-  const int grid = (int)(want < cap ? want : cap);
-  /* the work buffers of the resident warps (Jacobian columns, FD cost derivatives, line-search candidates) */
-  const long long slots = (long long)grid * kGroupsPerCta;
-  if (slots > h->slots) {
-    CU(h, cudaStreamSynchronize(h->stream));
-    void **bufs[] = {&h->slotF, &h->slotC, &h->slotCandX, &h->slotCandU};
-    const size_t T = (size_t)h->desc.T, na = (size_t)h->desc.params.n_alpha;
-    const size_t per[] = {T * (N + M) * N, CD == kCostFD ? T * Scratch<N, M, S, CD>::NCF : 0, na * T * N, na * T * M};
-    for (int i = 0; i < 4; i++) {
-      if (*bufs[i]) CU(h, cudaFree(*bufs[i]));
-      *bufs[i] = nullptr;
-      if (per[i]) CU(h, cudaMalloc(bufs[i], per[i] * sizeof(S) * (size_t)slots));
-    }
-    h->slots = slots;
-  }
-  a.P.bulk_f = ((size_t)h->slotF % 16 == 0) && (((size_t)h->desc.T * (N + M) * N * sizeof(S)) % 16 == 0) &&
-               (((size_t)kTileB * (N + M) * N * sizeof(S)) % 16 == 0);
-  {
-    constexpr size_t ncf = Scratch<N, M, S, CD>::NCF;
-    a.P.bulk_c = CD == kCostFD && ((size_t)h->slotC % 16 == 0) && (((size_t)h->desc.T * ncf * sizeof(S)) % 16 == 0) &&
-                 (((size_t)kTileB * ncf * sizeof(S)) % 16 == 0);
-  }
-  a.slotF = (S *)h->slotF;
-  a.slotC = (S *)h->slotC;
-  a.slotCandX = (S *)h->slotCandX;
-  a.slotCandU = (S *)h->slotCandU;
-  CU(h, cudaMemsetAsync(h->queue, 0, sizeof(unsigned long long), h->stream));
-  kern<<<grid, kThreads, smem, h->stream>>>(a);
-  CU(h, cudaGetLastError());
-  h->launches++;
-  return ILQR_OK;
-}
-
-template <class Model, typename S>
-int launch_cd(ilqr_handle *h, int op, int n_iters, double scalar) {
-#if defined(ILQR_EXPERIMENT_BUILD) /* experiments only: acrobot f64 analytic, to keep the build short */
-  if (!(std::is_same<Model, Acrobot>::value && std::is_same<S, double>::value && h->desc.cost_deriv == ILQR_COST_ANALYTIC))
-    return fail(h, ILQR_E_INVALID, "experiment build: acrobot f64 analytic only");
-  if constexpr (std::is_same<Model, Acrobot>::value && std::is_same<S, double>::value) {
-    const bool pack16 = h->lanes == 16 || (h->lanes == 0 && h->desc.B >= 32768);
-    return pack16 ? launch_t<Model, S, kCostAnalytic, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostAnalytic, 32>(h, op, n_iters, scalar);
-  } else {
-    return ILQR_E_INVALID;
-  }
-#else
-  /* two trajectories per warp once the batch can fill the schedulers that way (4 warps per scheduler on 148 SMs) */
-  const bool pack = h->lanes == 16 || (h->lanes == 0 && h->desc.B >= 32768);
-  if (h->desc.cost_deriv == ILQR_COST_ANALYTIC)
-    return pack ? launch_t<Model, S, kCostAnalytic, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostAnalytic, 32>(h, op, n_iters, scalar);
-  return pack ? launch_t<Model, S, kCostFD, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostFD, 32>(h, op, n_iters, scalar);
-#endif
-}
-template <class Model>
-int launch_s(ilqr_handle *h, int op, int n_iters, double scalar) {
-  if (h->desc.dtype == ILQR_F32) return launch_cd<Model, float>(h, op, n_iters, scalar);
-  return launch_cd<Model, double>(h, op, n_iters, scalar);
-}
 int launch(ilqr_handle *h, int op, int n_iters, double scalar) {
   if (h->desc.model_id >= ILQR_MODEL_USER_BASE)
     return h->desc.dtype == ILQR_F32 ? launch_user<float>(h, op, n_iters, scalar) : launch_user<double>(h, op, n_iters, scalar);
-  if (h->desc.model_id == ILQR_MODEL_ACROBOT) return launch_s<Acrobot>(h, op, n_iters, scalar);
-  return launch_s<DoubleIntegrator>(h, op, n_iters, scalar);
+  if (h->desc.model_id == ILQR_MODEL_ACROBOT) return ilqr_launch_acrobot(h, op, n_iters, scalar);
+  return ilqr_launch_double_integrator(h, op, n_iters, scalar);
 }
 
 size_t state_size(const ilqr_handle *h) {

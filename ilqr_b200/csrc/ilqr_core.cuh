@@ -138,7 +138,7 @@ struct LaneRegs {
 
 #if defined(__CUDACC__)
 #if defined(ILQR_PHASE_CLOCKS)
-__device__ unsigned long long g_phase_clk[32], g_phase_cnt[32];
+static __device__ unsigned long long g_phase_clk[32], g_phase_cnt[32];
 #endif
 /* device: the calling thread is one lane; a phase ends with a warp barrier.
  *

@@ -40,7 +40,7 @@ namespace ilqr {
    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,  \
    2.08757232129817482790e-09, -1.13596475577881948265e-11 /* C1..C6 */}
 #if defined(__CUDACC__)
-__constant__ double kTrigDev[16] = ILQR_TRIG_TABLE;
+static __constant__ double kTrigDev[16] = ILQR_TRIG_TABLE; /* internal linkage: one copy per translation unit */
 #endif
 static const double kTrigHost[16] = ILQR_TRIG_TABLE;
 
@@ -124,7 +124,7 @@ struct SinCos {
   double s, c;
 };
 #if defined(__CUDACC__) && !defined(ILQR_SINCOS_SLOW_INLINE)
-__host__ __device__ __noinline__
+static __host__ __device__ __noinline__ /* internal linkage: the header is included by several translation units */
 #else
 ILQR_HD
 #endif
