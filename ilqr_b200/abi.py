@@ -15,6 +15,7 @@ MODEL_ACROBOT, MODEL_DOUBLE_INTEGRATOR = 0, 1
 MODEL_USER_BASE = 100  # ids of models registered at run time (register_model)
 F64, F32 = 0, 1
 COST_FD, COST_ANALYTIC = 0, 1
+FLAG_ENGINE_WARP = 1  # ilqr_desc.flags
 RUNNING, EXIT_GRAD, EXIT_TOLFUN, EXIT_LAMBDA_MAX, EXIT_MAXITER = 0, 1, 2, 3, 4
 STATUS_NAMES = {0: "RUNNING", 1: "GRAD", 2: "TOLFUN", 3: "LAMBDA_MAX", 4: "MAXITER"}
 
@@ -45,7 +46,8 @@ class Params(C.Structure):
 class Desc(C.Structure):
     _fields_ = [
         ("model_id", C.c_int32), ("dtype", C.c_int32), ("cost_deriv", C.c_int32), ("device", C.c_int32),
-        ("T", C.c_int32), ("override_limits", C.c_int32), ("B", C.c_int64), ("dt", C.c_double),
+        ("T", C.c_int32), ("override_limits", C.c_int32), ("flags", C.c_int32), ("reserved1", C.c_int32),
+        ("B", C.c_int64), ("dt", C.c_double),
         ("u_min", C.c_double * MAX_M), ("u_max", C.c_double * MAX_M),
         ("model_params", C.c_double * 16),
         ("params", Params),
@@ -76,9 +78,10 @@ MODEL_DIMS = {MODEL_ACROBOT: (4, 1), MODEL_DOUBLE_INTEGRATOR: (4, 2)}
 
 
 def make_desc(model=MODEL_ACROBOT, T=200, B=1, dt=0.02, dtype=F64, cost_deriv=COST_FD, device=0, u_min=None,
-              u_max=None, goal=None, params=None):
+              u_max=None, goal=None, params=None, flags=0):
     d = Desc()
     d.model_id, d.dtype, d.cost_deriv, d.device = model, dtype, cost_deriv, device
+    d.flags = int(flags)
     d.T, d.B, d.dt = int(T), int(B), float(dt)
     if (u_min is None) != (u_max is None):
         raise ValueError("give both u_min and u_max or neither")

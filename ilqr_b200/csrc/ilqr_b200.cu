@@ -182,9 +182,13 @@ int ilqr_destroy(ilqr_handle *h) {
     DeviceGuard g(h->desc.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *bufs[] = {h->x0, h->xs, h->us, h->K, h->k, h->Vx0, h->Vxx0, h->st, h->tmp, h->queue,
-                    h->slotF, h->slotC, h->slotCandX, h->slotCandU};
+                    h->slotF, h->slotC, h->slotCandX, h->slotCandU,
+                    h->phF, h->phC, h->phCandX, h->phCandU, h->phNewcost, h->phAct, h->phNact};
     for (void *b : bufs)
       if (b) cudaFree(b);
+    if (h->phHostCount) cudaFreeHost(h->phHostCount);
+    for (cudaEvent_t e : h->phEvent)
+      if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -201,6 +205,7 @@ int ilqr_create(const ilqr_desc *desc, ilqr_handle **out) {
     return fail(nullptr, ILQR_E_INVALID, "unknown cost_deriv");
   if (desc->B < 1 || desc->T < 1) return fail(nullptr, ILQR_E_INVALID, "B and T must be positive");
   if (!(desc->dt > 0)) return fail(nullptr, ILQR_E_INVALID, "dt must be positive");
+  if ((desc->flags & ~ILQR_FLAG_ALL) != 0 || desc->reserved1 != 0) return fail(nullptr, ILQR_E_INVALID, "unknown flags");
   {
     SolveParams<double> chk;
     if (make_solve_params<double>(*desc, &chk) != 0) return fail(nullptr, ILQR_E_INVALID, "bad solver parameters");
@@ -213,6 +218,9 @@ int ilqr_create(const ilqr_desc *desc, ilqr_handle **out) {
   if (!h) return fail(nullptr, ILQR_E_NOMEM, "out of host memory");
   h->desc = *desc;
   if (const char *e = getenv("ILQR_B200_LANES")) h->lanes = atoi(e) == 16 ? 16 : (atoi(e) == 32 ? 32 : 0);
+  h->engine_warp = (desc->flags & ILQR_FLAG_ENGINE_WARP) != 0;
+  if (const char *e = getenv("ILQR_B200_ENGINE")) h->engine_warp = strcmp(e, "warp") == 0 || (h->engine_warp && strcmp(e, "phase") != 0);
+  if (h->lanes != 0) h->engine_warp = true; /* a forced lane decomposition is a property of the warp kernel */
   h->n = n;
   h->m = m;
   h->ssize = desc->dtype == ILQR_F32 ? 4 : 8;
@@ -271,6 +279,9 @@ int ilqr_iterate(ilqr_handle *h, int n_iters) {
   if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_iterate before ilqr_set_initial");
   if (n_iters < 0) return fail(h, ILQR_E_INVALID, "n_iters must be >= 0");
   DeviceGuard g(h->desc.device);
+  if (!h->engine_warp && h->desc.model_id < ILQR_MODEL_USER_BASE) /* the batch-lockstep phase kernels (ilqr_phases.cuh) */
+    return h->desc.model_id == ILQR_MODEL_ACROBOT ? ilqr_phase_iterate_acrobot(h, n_iters)
+                                                  : ilqr_phase_iterate_double_integrator(h, n_iters);
   return launch(h, kOpIterate, n_iters, 0.0);
 }
 
@@ -350,6 +361,6 @@ int ilqr_make_inputs(uint64_t seed, int64_t B, int32_t T, int32_t n, int32_t m, 
   return ILQR_OK;
 }
 
-const char *ilqr_version(void) { return "ilqr_b200 0.1 sm_100a warp-per-trajectory f64/f32"; }
+const char *ilqr_version(void) { return "ilqr_b200 0.2 sm_100a batch-lockstep phase kernels + warp-per-trajectory kernel, f64/f32"; }
 
 }  // extern "C"

@@ -78,6 +78,7 @@ template <typename S>
 struct TrajState {
   S cost, lam, dlam, dV0, dV1, gnorm, dcost, expected, alpha, new_cost;
   int iter, trips, status, alpha_index, n_accept, n_reject, n_backward, diverge, flg_change, n_rollouts, n_deriv;
+  int roll; /* phase engine (ilqr_phases.cuh): what the backward phase decided for this trip's line search */
 };
 
 /* base pointers of one trajectory's arrays (contiguous in t) */
@@ -338,7 +339,9 @@ struct Core {
   ILQR_HD static int ix_cux(int j, int i) { return NM + (N + j) * NM + i; }
   ILQR_HD static int ix_cuu(int i, int j) { return NM + (N + i) * NM + N + j; }
 
-  ILQR_HD void cost_stencil(int o, bool terminal, const S *x, const S *u, S *cf) {
+  ILQR_HD void cost_stencil(int o, bool terminal, const S *x, const S *u, S *cf) { cost_stencil_s(P, o, terminal, x, u, cf); }
+  /* the same without an instance (the phase kernels of ilqr_phases.cuh run one stencil output per thread) */
+  ILQR_HD static void cost_stencil_s(const SolveParams<S> &P, int o, bool terminal, const S *x, const S *u, S *cf) {
     const S eps = P.fd_eps;
     const S *mp = P.mp;
     S xa[N], ua[M];
@@ -414,7 +417,8 @@ struct Core {
   }
 
   /* closed-form cost derivatives of the model twin in the full layout (one lane; terminal step only) */
-  ILQR_HD void analytic_cost(const S *x, const S *u, bool terminal, S *cf) {
+  ILQR_HD void analytic_cost(const S *x, const S *u, bool terminal, S *cf) { analytic_cost_s(P, x, u, terminal, cf); }
+  ILQR_HD static void analytic_cost_s(const SolveParams<S> &P, const S *x, const S *u, bool terminal, S *cf) {
     for (int c = 0; c < NM; c++) cf[c] = Model::cost_d1(c, x, u, P.mp, terminal);
     for (int c = 0; c < NM; c++)
       for (int d = 0; d < NM; d++) cf[NM + c * NM + d] = Model::cost_d2(c, d, x, u, P.mp, terminal);

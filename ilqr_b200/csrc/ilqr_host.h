@@ -24,6 +24,13 @@ struct ilqr_handle {
   void *slotF = nullptr, *slotC = nullptr, *slotCandX = nullptr, *slotCandU = nullptr; /* per resident warp */
   long long slots = 0;
   int lanes = 0; /* 0: choose by batch size; 16 / 32: forced (environment ILQR_B200_LANES, for experiments and tests) */
+  /* batch-lockstep phase engine (ilqr_phases.cuh): per-trajectory work arrays, active lists, trip bookkeeping */
+  bool engine_warp = false; /* ILQR_FLAG_ENGINE_WARP or environment ILQR_B200_ENGINE=warp */
+  void *phF = nullptr, *phC = nullptr, *phCandX = nullptr, *phCandU = nullptr, *phNewcost = nullptr;
+  int *phAct = nullptr, *phNact = nullptr;
+  int *phHostCount = nullptr; /* pinned: active-list lengths read back while the trips run */
+  cudaEvent_t phEvent[2] = {nullptr, nullptr};
+  bool phReady = false;
   unsigned long long *queue = nullptr;
   int num_sms = 0;
   int64_t launches = 0;
@@ -44,5 +51,8 @@ int ilqr_fail(ilqr_handle *h, int code, const std::string &msg);
 /* one launch of the solver kernel of a built-in model for the handle's dtype / derivative mode / batch size */
 int ilqr_launch_acrobot(ilqr_handle *h, int op, int n_iters, double scalar);
 int ilqr_launch_double_integrator(ilqr_handle *h, int op, int n_iters, double scalar);
+/* up to n_iters loop trips for every running instance on the phase engine (ilqr_phase_launch.cuh) */
+int ilqr_phase_iterate_acrobot(ilqr_handle *h, int n_iters);
+int ilqr_phase_iterate_double_integrator(ilqr_handle *h, int n_iters);
 
 #endif

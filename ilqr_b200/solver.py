@@ -22,10 +22,10 @@ class BatchILQR:
     """`new iLQR(model, dt)` for B instances (include/ilqr.h:30-44)."""
 
     def __init__(self, model=abi.MODEL_ACROBOT, T=200, B=1, dt=0.02, dtype=abi.F64, cost_deriv=abi.COST_FD,
-                 device=0, u_min=None, u_max=None, goal=None, params=None, model_params=None):
+                 device=0, u_min=None, u_max=None, goal=None, params=None, model_params=None, flags=0):
         self.lib = abi.load()
         self.desc = abi.make_desc(model=model, T=T, B=B, dt=dt, dtype=dtype, cost_deriv=cost_deriv, device=device,
-                                  u_min=u_min, u_max=u_max, goal=goal, params=params)
+                                  u_min=u_min, u_max=u_max, goal=goal, params=params, flags=flags)
         if model_params is not None:  # ilqr_desc.model_params[0..15]: what a registered model's functions see as `mp`
             for i, v in enumerate(model_params):
                 self.desc.model_params[i] = float(v)

@@ -49,6 +49,11 @@ extern "C" {
 #define ILQR_COST_FD 0        /* the reference's stencils, src/derivatives.cpp:29-144, include/finite_diff.h:22-86 */
 #define ILQR_COST_ANALYTIC 1  /* closed form from the model twin (BASELINE configs 2, 3, 5) */
 
+/* ilqr_desc.flags */
+#define ILQR_FLAG_ENGINE_WARP 1    /* run ilqr_iterate / ilqr_solve on the persistent warp-per-trajectory kernel instead of
+                                      the batch-lockstep phase kernels (identical results) */
+#define ILQR_FLAG_ALL (ILQR_FLAG_ENGINE_WARP)
+
 /* error codes */
 #define ILQR_OK 0
 #define ILQR_E_INVALID -1   /* bad argument / unsupported combination */
@@ -95,6 +100,8 @@ typedef struct ilqr_desc {
   int32_t device;     /* CUDA device ordinal */
   int32_t T;          /* number of controls = u0.size() (src/ilqr_core.cpp:12); knots = T+1 */
   int32_t override_limits; /* 0: the model's own u_min/u_max (acrobot.h:37, double_integrator.h:25-26) */
+  int32_t flags;      /* ILQR_FLAG_* bits; 0 = the reference's behaviour on the default engine */
+  int32_t reserved1;  /* must be 0 */
   int64_t B;          /* number of independent problem instances */
   double dt;          /* iLQR(Model*, double timeDelta), include/ilqr.h:30 */
   double u_min[ILQR_MAX_M];

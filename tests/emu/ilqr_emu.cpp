@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../ilqr_b200/csrc/ilqr_core.cuh"
+#include "../../ilqr_b200/csrc/ilqr_phases.cuh"
 #include "../../ilqr_b200/csrc/params.h"
 
 using namespace ilqr;
@@ -97,7 +98,43 @@ struct Emu : EmuBase {
     core().op_warm_start();
     return st.cost;
   }
-  void iterate(int cnt) override { core().op_iterate(cnt); }
+  void iterate(int cnt) override {
+    if (phases) iterate_phases(cnt);
+    else core().op_iterate(cnt);
+  }
+  /* The batch-lockstep engine (ilqr_phases.cuh) on one trajectory: what phase_begin / sweep / backward / rollout /
+   * accept kernels do per trip, every thread's task run in turn by the same ILQR_HD functions the kernels call. */
+  bool phases = false;
+  void iterate_phases(int cnt) {
+    using Ph = Phases<Model, S, CD>;
+    const TrajPtrs<S> tr = ptrs();
+    if (st.status == kRunning && st.iter >= P.max_iter) st.status = kExitMaxIter;
+    bool run = st.status == kRunning;
+    const int na = P.n_alpha;
+    S newcost[kMaxAlpha] = {0};
+    for (int trip = 0; trip < cnt && run; trip++) {
+      if (st.flg_change || trip == 0) {
+        for (int part = 0; part < Ph::kParts; part++)
+          for (int t = 0; t < T; t++) Ph::sweep_task(P, xs.data(), us.data(), bufF.data(), part, t);
+        if (CD == kCostFD)
+          for (int o = 0; o < Ph::kStencilStep; o++)
+            for (int t = 0; t < T; t++) Ph::stencil_task(P, xs.data(), us.data(), bufC.data(), o, t);
+      }
+      Ph::backward_trip(P, tr, bufF.data(), bufC.data(), st);
+      if (st.roll == kRollGo)
+        for (int a = 0; a < na; a++) newcost[a] = Ph::rollout_task(P, tr, candX.data(), candU.data(), a);
+      if (st.status != kRunning) break;
+      const bool fwd = Ph::accept(P, st, newcost);
+      if (fwd) {
+        const int ai = st.alpha_index;
+        for (int t = 0; t < T; t++) {
+          for (int c = 0; c < N; c++) xs[(size_t)(t + 1) * N + c] = candX[((size_t)t * na + ai) * N + c];
+          for (int c = 0; c < M; c++) us[(size_t)t * M + c] = candU[((size_t)t * na + ai) * M + c];
+        }
+      }
+      run = Ph::schedule(P, st, fwd);
+    }
+  }
   int backward_once(double lam) override {
     core().op_backward_once(S(lam));
     return st.diverge;
@@ -152,10 +189,21 @@ struct Emu : EmuBase {
   }
 };
 
-int g_lanes = 32; /* lanes per trajectory of the next emu_new: 32 (one trajectory per warp) or 16 (two per warp) */
+int g_lanes = 32; /* lanes per trajectory of the next emu_new: 32 (one trajectory per warp), 16 (two per warp), or
+                    1 = the batch-lockstep phase engine (one thread per task) */
 
 template <class Model, typename S>
 EmuBase *make_cd(const ilqr_desc &d) {
+  if (g_lanes == 1) { /* the phase engine: thread-per-task functions of ilqr_phases.cuh */
+    if (d.cost_deriv == ILQR_COST_ANALYTIC) {
+      auto *e = new Emu<Model, S, kCostAnalytic, 32>(d);
+      e->phases = true;
+      return e;
+    }
+    auto *e = new Emu<Model, S, kCostFD, 32>(d);
+    e->phases = true;
+    return e;
+  }
   if (g_lanes == 16) {
     if (d.cost_deriv == ILQR_COST_ANALYTIC) return new Emu<Model, S, kCostAnalytic, 16>(d);
     return new Emu<Model, S, kCostFD, 16>(d);
@@ -203,7 +251,7 @@ int run_qp(const ilqr_params &p, int generic, const double *Q, const double *c, 
 
 extern "C" {
 
-void emu_set_lanes(int lanes) { g_lanes = lanes == 16 ? 16 : 32; }
+void emu_set_lanes(int lanes) { g_lanes = lanes == 16 ? 16 : (lanes == 1 ? 1 : 32); }
 
 void *emu_new(const ilqr_desc *d) {
   if (d->model_id == ILQR_MODEL_ACROBOT) return make_dtype<Acrobot>(*d);

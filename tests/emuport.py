@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(ROOT, "tests", "_build", "libilqr_emu.so")            # 
 LIB_PATH_LIBM = os.path.join(ROOT, "tests", "_build", "libilqr_emu_libm.so")  # platform libm sin/cos (= the oracle's)
 SRC = os.path.join(ROOT, "tests", "emu", "ilqr_emu.cpp")
 DEPS = [SRC] + [os.path.join(ROOT, "ilqr_b200", "csrc", f) for f in
-                ("ilqr_core.cuh", "boxqp.cuh", "models.cuh", "trig.cuh", "params.h")] + [os.path.join(ROOT, "include", "ilqr_b200.h")]
+                ("ilqr_core.cuh", "ilqr_phases.cuh", "boxqp.cuh", "models.cuh", "trig.cuh", "params.h")] + [os.path.join(ROOT, "include", "ilqr_b200.h")]
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 _libs = {}
@@ -74,7 +74,7 @@ class EmuSolver:
     def __init__(self, model=abi.MODEL_ACROBOT, dt=0.02, goal=None, u_min=None, u_max=None,
                  cost_deriv=abi.COST_FD, params=None, dtype=abi.F64, libm=False, lanes=32):
         self.L = lib(libm)
-        self.L.emu_set_lanes(int(lanes))  # 32: one trajectory per warp; 16: the two-per-warp lane decomposition
+        self.L.emu_set_lanes(int(lanes))  # 32: one trajectory per warp; 16: two per warp; 1: the phase engine (ilqr_phases.cuh)
         self.desc = abi.make_desc(model=model, dt=dt, goal=goal, u_min=u_min, u_max=u_max, cost_deriv=cost_deriv,
                                   params=params, dtype=dtype)
         self.h = self.L.emu_new(C.byref(self.desc))

@@ -82,6 +82,24 @@ def test_sixteen_lane_decomposition_equals_oracle_bit_for_bit(golden_solver, cas
     lockstep(model, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), True, lanes=16, cost_deriv=cd, **kw)
 
 
+@pytest.mark.parametrize("case,model,cd,kw", [
+    ("acrobot_T200_b0", abi.MODEL_ACROBOT, abi.COST_FD, {}), ("acrobot_T200_b1", abi.MODEL_ACROBOT, abi.COST_ANALYTIC, {}),
+    ("acrobot_T200_b2", abi.MODEL_ACROBOT, abi.COST_ANALYTIC, {}), ("acrobot_T200_b5", abi.MODEL_ACROBOT, abi.COST_FD, {}),
+    ("acrobot_lim15_T200_b0", abi.MODEL_ACROBOT, abi.COST_FD, dict(u_min=[-1.5], u_max=[1.5])),
+    ("acrobot_lim15_T200_b2", abi.MODEL_ACROBOT, abi.COST_ANALYTIC, dict(u_min=[-1.5], u_max=[1.5])),
+    ("acrobot_cli_T499", abi.MODEL_ACROBOT, abi.COST_FD, {}),
+    ("integrator_cli_T99", abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, None),
+    ("integrator_rand_T60_b0", abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_ANALYTIC, None),
+    ("integrator_rand_T60_b2", abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, None)])
+def test_phase_engine_source_equals_oracle_bit_for_bit(golden_solver, case, model, cd, kw):
+    """the batch-lockstep engine (ilqr_b200/csrc/ilqr_phases.cuh: one thread per sweep task / trajectory / candidate):
+    the functions its kernels call, run task by task on the CPU, reproduce the oracle bit for bit at every trip"""
+    g = golden_solver
+    if kw is None:
+        kw = dict(goal=list(g[case + "/goal"]))
+    lockstep(model, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), True, lanes=1, cost_deriv=cd, **kw)
+
+
 def test_warm_start_kernel_source_equals_oracle():
     rng = np.random.default_rng(3)
     x0, u0 = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (90, 1))

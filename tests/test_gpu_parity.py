@@ -215,6 +215,67 @@ def test_acrobot_bit_exact_vs_kernel_source_on_cpu(cost_deriv, limits):
 
 
 # ---------------------------------------------------------------------------------------------
+# the two engines: batch-lockstep phase kernels (default) and the persistent warp-per-trajectory kernel
+# ---------------------------------------------------------------------------------------------
+ALL_FIELDS = ("xs", "us", "K", "k", "cost", "lambda", "dlambda", "dV", "gnorm", "Vx0", "Vxx0", "iters", "status",
+              "alpha_index", "n_accept", "n_reject", "n_backward", "diverge")
+
+
+@pytest.mark.parametrize("model,cd,dtype,T,B,kw", [
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F64, 200, 300, {}),
+    (abi.MODEL_ACROBOT, abi.COST_FD, abi.F64, 200, 70, {}),
+    (abi.MODEL_ACROBOT, abi.COST_FD, abi.F64, 200, 70, dict(u_min=[-1.5], u_max=[1.5])),
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F32, 500, 70, {}),
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F64, 37, 33, {}),
+    (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, abi.F64, 60, 40, dict(goal=[1.0, 1.0, 0.0, 0.0])),
+    (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_ANALYTIC, abi.F64, 99, 40, dict(goal=[0.5, -0.5, 0.0, 0.0])),
+    (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_ANALYTIC, abi.F32, 60, 40, dict(goal=[1.0, 1.0, 0.0, 0.0])),
+])
+def test_phase_engine_equals_warp_engine_bit_for_bit(model, cd, dtype, T, B, kw):
+    """Both engines run the same arithmetic entry for entry (ilqr_phases.cuh uses Core's helpers), so every array,
+    scalar and counter must agree BIT FOR BIT at every checkpoint up to termination, in every mode and dtype."""
+    n, m = abi.MODEL_DIMS[model]
+    x0, u0 = make_inputs(2024, B, T, n, m)
+    dt = 0.02 if model == abi.MODEL_ACROBOT else 0.05
+    ph = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, **kw)
+    wp = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, flags=abi.FLAG_ENGINE_WARP, **kw)
+    ph.set_initial(x0, u0)
+    wp.set_initial(x0, u0)
+    done = 0
+    for n_it in (1, 4, 15, 101):
+        ph.iterate(n_it - done)
+        wp.iterate(n_it - done)
+        done = n_it
+        for f in ALL_FIELDS:
+            a, b = ph.get(f), wp.get(f)
+            assert np.array_equal(a, b), (n_it, f, int((a != b).reshape(B, -1).any(axis=1).sum()))
+    assert (ph.get("status") != abi.RUNNING).all()
+    # the phase engine really ran its own kernels: four launches per trip, not one per iterate call
+    assert ph.launch_count > wp.launch_count + 8
+
+
+def test_phase_engine_iterate_resume_and_warm_start():
+    """iterate in uneven chunks (active list rebuilt by each call), then warm start and continue: equal to one call"""
+    B, T = 96, 120
+    x0, u0 = make_inputs(31, B, T, 4, 1)
+    a = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    b = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC, flags=abi.FLAG_ENGINE_WARP)
+    for s in (a, b):
+        s.set_initial(x0, u0)
+    for chunk in (3, 1, 9, 2):
+        a.iterate(chunk)
+    b.iterate(15)
+    for f in ALL_FIELDS:
+        assert np.array_equal(a.get(f), b.get(f)), f
+    for s in (a, b):
+        s.warm_start(x0 + 0.01)
+        s.iterate(0)
+        s.iterate(6)
+    for f in ALL_FIELDS:
+        assert np.array_equal(a.get(f), b.get(f)), f
+
+
+# ---------------------------------------------------------------------------------------------
 # control-limited acrobot (BASELINE config 4): boxQP path hot, lambda-max exits
 # ---------------------------------------------------------------------------------------------
 def test_acrobot_control_limited(golden_solver):
