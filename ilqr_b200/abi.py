@@ -100,7 +100,7 @@ _lib = None
 
 EXPORTS = [
     "ilqr_default_params", "ilqr_model_info", "ilqr_create", "ilqr_destroy", "ilqr_last_error",
-    "ilqr_set_initial", "ilqr_warm_start", "ilqr_iterate", "ilqr_solve", "ilqr_backward_once",
+    "ilqr_set_initial", "ilqr_warm_start", "ilqr_resume", "ilqr_iterate", "ilqr_solve", "ilqr_backward_once",
     "ilqr_rollout_once", "ilqr_get", "ilqr_sync", "ilqr_stream", "ilqr_launch_count", "ilqr_make_inputs",
     "ilqr_version", "ilqr_register_model", "ilqr_compile_model",
 ]
@@ -125,6 +125,7 @@ def load():
     L.ilqr_last_error.argtypes = [vp]
     L.ilqr_set_initial.argtypes = [vp, vp, vp, C.c_int]
     L.ilqr_warm_start.argtypes = [vp, vp, C.c_int]
+    L.ilqr_resume.argtypes = [vp]
     L.ilqr_iterate.argtypes = [vp, C.c_int]
     L.ilqr_solve.argtypes = [vp]
     L.ilqr_backward_once.argtypes = [vp, C.c_double]

@@ -63,6 +63,16 @@ __global__ void ilqr_gather_kernel(const TrajState<S> *st, long long B, int fiel
   }
 }
 
+/* iLQR::generate_trajectory() re-entered (src/ilqr_core.cpp:88-102): iter = 0, flgChange = true, running again */
+template <typename S>
+__global__ void ilqr_resume_kernel(TrajState<S> *st, long long B) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  st[b].iter = 0;
+  st[b].flg_change = 1;
+  st[b].status = kRunning;
+}
+
 thread_local std::string g_create_error;
 
 }  // namespace
@@ -183,7 +193,7 @@ int ilqr_destroy(ilqr_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *bufs[] = {h->x0, h->xs, h->us, h->K, h->k, h->Vx0, h->Vxx0, h->st, h->tmp, h->queue,
                     h->slotF, h->slotC, h->slotCandX, h->slotCandU,
-                    h->phF, h->phC, h->phCandX, h->phCandU, h->phNewcost, h->phAct, h->phNact};
+                    h->phF, h->phC, h->phCandX, h->phCandU, h->phNewcost, h->phGterm, h->phAct, h->phNact};
     for (void *b : bufs)
       if (b) cudaFree(b);
     if (h->phHostCount) cudaFreeHost(h->phHostCount);
@@ -283,6 +293,19 @@ int ilqr_iterate(ilqr_handle *h, int n_iters) {
     return h->desc.model_id == ILQR_MODEL_ACROBOT ? ilqr_phase_iterate_acrobot(h, n_iters)
                                                   : ilqr_phase_iterate_double_integrator(h, n_iters);
   return launch(h, kOpIterate, n_iters, 0.0);
+}
+
+int ilqr_resume(ilqr_handle *h) {
+  if (!h) return ILQR_E_INVALID;
+  if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_resume before ilqr_set_initial");
+  DeviceGuard g(h->desc.device);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((h->desc.B + threads - 1) / threads);
+  if (h->desc.dtype == ILQR_F32) ilqr_resume_kernel<float><<<blocks, threads, 0, h->stream>>>((TrajState<float> *)h->st, h->desc.B);
+  else ilqr_resume_kernel<double><<<blocks, threads, 0, h->stream>>>((TrajState<double> *)h->st, h->desc.B);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return ILQR_OK;
 }
 
 int ilqr_solve(ilqr_handle *h) {

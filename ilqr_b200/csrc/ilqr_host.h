@@ -26,7 +26,7 @@ struct ilqr_handle {
   int lanes = 0; /* 0: choose by batch size; 16 / 32: forced (environment ILQR_B200_LANES, for experiments and tests) */
   /* batch-lockstep phase engine (ilqr_phases.cuh): per-trajectory work arrays, active lists, trip bookkeeping */
   bool engine_warp = false; /* ILQR_FLAG_ENGINE_WARP or environment ILQR_B200_ENGINE=warp */
-  void *phF = nullptr, *phC = nullptr, *phCandX = nullptr, *phCandU = nullptr, *phNewcost = nullptr;
+  void *phF = nullptr, *phC = nullptr, *phCandX = nullptr, *phCandU = nullptr, *phNewcost = nullptr, *phGterm = nullptr;
   int *phAct = nullptr, *phNact = nullptr;
   int *phHostCount = nullptr; /* pinned: active-list lengths read back while the trips run */
   cudaEvent_t phEvent[2] = {nullptr, nullptr};

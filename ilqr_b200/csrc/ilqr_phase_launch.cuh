@@ -6,6 +6,8 @@
 #ifndef ILQR_PHASE_LAUNCH_CUH_
 #define ILQR_PHASE_LAUNCH_CUH_
 
+#include <stdlib.h>
+
 #include "ilqr_host.h"
 #include "ilqr_phases.cuh"
 #include "params.h"
@@ -24,6 +26,7 @@ int phase_prepare(ilqr_handle *h) {
   CU(h, cudaMalloc(&h->phCandX, B * T * na * N * sizeof(S)));
   CU(h, cudaMalloc(&h->phCandU, B * T * na * M * sizeof(S)));
   CU(h, cudaMalloc(&h->phNewcost, B * kMaxAlpha * sizeof(S)));
+  CU(h, cudaMalloc(&h->phGterm, B * T * sizeof(S)));
   CU(h, cudaMalloc((void **)&h->phAct, 2 * B * sizeof(int)));
   CU(h, cudaMalloc((void **)&h->phNact, 2 * sizeof(int)));
   CU(h, cudaMallocHost((void **)&h->phHostCount, 2 * sizeof(int)));
@@ -51,6 +54,7 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
   a.buf.cand_x = (S *)h->phCandX;
   a.buf.cand_u = (S *)h->phCandU;
   a.buf.newcost = (S *)h->phNewcost;
+  a.buf.gterm = (S *)h->phGterm;
   a.buf.act = h->phAct;
   a.buf.n_act = h->phNact;
   a.B = h->desc.B;
@@ -64,18 +68,62 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
     h->launches++;
   }
   long long bound = a.B; /* upper bound of the active count: it never grows */
+  /* the head of a trip (sweep + backward) runs one thread per trajectory when the active set can fill the machine that
+   * way, one warp per trajectory below that (ilqr_phases.cuh: phase_pre_warp_kernel) */
+  long long warp_pre_max = 0, rows_max = 24576;
+  if (const char *e = getenv("ILQR_B200_WARP_PRE_MAX")) warp_pre_max = atoll(e);
+  if (const char *e = getenv("ILQR_B200_ROWS_MAX")) rows_max = atoll(e);
+  int rows_gpw = 4;
+  if (const char *e = getenv("ILQR_B200_ROWS_GPW")) rows_gpw = atoi(e);
+  /* below this many running trajectories the lockstep rounds stop and the persistent warp-per-trajectory kernel
+   * finishes the solve: every trajectory then advances at its own pace instead of the pace of the slowest */
+  long long handover = 0;
+  if (const char *e = getenv("ILQR_B200_HANDOVER")) handover = atoll(e);
+  int check_every = kPhaseCheckEvery;
+  if (const char *e = getenv("ILQR_B200_CHECK_EVERY")) check_every = atoi(e) > 0 ? atoi(e) : check_every;
+  constexpr int N = Model::N, M = Model::M;
+  const size_t pre_smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S, 32>>::Sc, S>(h->desc.T) * kWarpsPerCta;
+  if (pre_smem > 48 * 1024)
+    CU(h, cudaFuncSetAttribute(phase_pre_warp_kernel<Model, S, CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem));
+  a.P.bulk_f = ((size_t)h->phF % 16 == 0) && (((size_t)h->desc.T * (N + M) * N * sizeof(S)) % 16 == 0) &&
+               (((size_t)kTileB * (N + M) * N * sizeof(S)) % 16 == 0);
+  {
+    constexpr size_t ncf = Scratch<N, M, S, CD>::NCF;
+    a.P.bulk_c = CD == kCostFD && ((size_t)h->phC % 16 == 0) && (((size_t)h->desc.T * ncf * sizeof(S)) % 16 == 0) &&
+                 (((size_t)kTileB * ncf * sizeof(S)) % 16 == 0);
+  }
   const int max_trips = n_iters < h->desc.params.max_iter + 1 ? n_iters : h->desc.params.max_iter + 1;
   const int na = h->desc.params.n_alpha;
   int pending = -1; /* slot of a read-back in flight */
-  for (int trip = 0; trip < max_trips && bound > 0; trip++) {
+  int trip = 0;
+  for (; trip < max_trips && bound > handover; trip++) {
     a.parity = trip & 1;
     a.force_sweep = trip == 0;
-    phase_sweep_kernel<Model, S, CD><<<(unsigned)bound, kSweepThreads, 0, st>>>(a);
-    phase_backward_kernel<Model, S, CD><<<(unsigned)((bound + kBackwardThreads - 1) / kBackwardThreads), kBackwardThreads, 0, st>>>(a);
+    if (bound <= warp_pre_max) { /* few trajectories: 32 lanes each (sweep + backward in one kernel) */
+      phase_pre_warp_kernel<Model, S, CD><<<(unsigned)((bound + kWarpsPerCta - 1) / kWarpsPerCta), kThreads, pre_smem, st>>>(a);
+      h->launches += 1;
+    } else if (bound <= rows_max) { /* a few thousand: 8 lanes each, one row of the Q-function per lane */
+      phase_sweep_kernel<Model, S, CD><<<(unsigned)bound, kSweepThreads, 0, st>>>(a);
+      if (rows_gpw == 1) {
+        constexpr int per_cta = (kRowThreads / 32) * 1;
+        phase_backward_rows_kernel<Model, S, CD, 1><<<(unsigned)((bound + per_cta - 1) / per_cta), kRowThreads, 0, st>>>(a);
+      } else if (rows_gpw == 2) {
+        constexpr int per_cta = (kRowThreads / 32) * 2;
+        phase_backward_rows_kernel<Model, S, CD, 2><<<(unsigned)((bound + per_cta - 1) / per_cta), kRowThreads, 0, st>>>(a);
+      } else {
+        constexpr int per_cta = (kRowThreads / 32) * 4;
+        phase_backward_rows_kernel<Model, S, CD, 4><<<(unsigned)((bound + per_cta - 1) / per_cta), kRowThreads, 0, st>>>(a);
+      }
+      h->launches += 2;
+    } else {
+      phase_sweep_kernel<Model, S, CD><<<(unsigned)bound, kSweepThreads, 0, st>>>(a);
+      phase_backward_kernel<Model, S, CD><<<(unsigned)((bound + kBackwardThreads - 1) / kBackwardThreads), kBackwardThreads, 0, st>>>(a);
+      h->launches += 2;
+    }
     phase_rollout_kernel<Model, S, CD><<<(unsigned)((bound * na + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
     phase_accept_kernel<Model, S, CD><<<(unsigned)((bound * 32 + kAcceptThreads - 1) / kAcceptThreads), kAcceptThreads, 0, st>>>(a);
-    h->launches += 4;
-    if ((trip + 1) % kPhaseCheckEvery == 0) {
+    h->launches += 2;
+    if ((trip + 1) % check_every == 0) {
       if (pending >= 0) { /* the count of kPhaseCheckEvery trips ago: by now it has almost always arrived */
         CU(h, cudaEventSynchronize(h->phEvent[pending]));
         bound = h->phHostCount[pending];
@@ -87,6 +135,11 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
     }
   }
   CU(h, cudaGetLastError());
+  if (bound > 0 && trip < max_trips) { /* hand the survivors to the persistent kernel for their remaining trips */
+    const int left = n_iters - trip;
+    return Model::M == 1 && Model::N == 4 && h->desc.model_id == ILQR_MODEL_ACROBOT ? ilqr_launch_acrobot(h, kOpIterate, left, 0.0)
+                                                                                     : ilqr_launch_double_integrator(h, kOpIterate, left, 0.0);
+  }
   return ILQR_OK;
 }
 

@@ -35,6 +35,9 @@
 #define ILQR_PHASES_CUH_
 
 #include "ilqr_core.cuh"
+#if defined(__CUDACC__)
+#include "ilqr_kernel.cuh"
+#endif
 
 namespace ilqr {
 
@@ -43,6 +46,26 @@ struct NoExec {
 };
 
 enum { kRollStop = 0, kRollGo = 1, kRollSkip = 2 }; /* TrajState::roll */
+
+/* One thread per trajectory means the lanes of a warp take different branches inside the boxQP of a timestep.  They
+ * must come back together before the next timestep's (identical) arithmetic: left to the compiler, the loop with its
+ * early exits reconverged only at the end of the kernel and every lane ran the whole recursion alone (ncu: 1.16
+ * threads per instruction, 5.4 ms per backward launch instead of 0.14).  `mask` = the lanes that carry a trajectory. */
+ILQR_HD void reconverge(unsigned mask) {
+#if defined(__CUDA_ARCH__)
+  __syncwarp(mask);
+#else
+  (void)mask;
+#endif
+}
+ILQR_HD bool lanes_any(unsigned mask, bool p) {
+#if defined(__CUDA_ARCH__)
+  return __any_sync(mask, p) != 0;
+#else
+  (void)mask;
+  return p;
+#endif
+}
 
 /* dst[0..CNT) = src[0..CNT).  `src` points into a dense array of CNT-element runs whose base is 256-byte aligned, so
  * when a run is a multiple of 16 bytes every run is 16-byte aligned and moves as 128-bit accesses. */
@@ -118,6 +141,7 @@ struct PhaseBufs {
   S *cand_x;  /* [B][T][n_alpha][n]  candidate states x_1..x_T */
   S *cand_u;  /* [B][T][n_alpha][m]  candidate controls */
   S *newcost; /* [B][kMaxAlpha]      */
+  S *gterm;   /* [B][T]              per-timestep terms of the gradient norm, written by the backward phase */
   int *act;   /* [2][B]              active lists, double-buffered by trip parity */
   int *n_act; /* [2]                 their lengths */
 };
@@ -182,9 +206,12 @@ struct Phases {
 
   /* iLQR::backward_pass (src/ilqr_core.cpp:350-401) for one trajectory, by ONE thread, everything in registers.
    * Returns the failing timestep or 0 (:371,400).  Entry for entry the arithmetic of Core::backward_step. */
-  ILQR_HD static int backward_pass(const SolveParams<S> &P, const TrajPtrs<S> &tr, const S *F, const S *Cfd, S lam, S &dV0,
-                                   S &dV1) {
+  ILQR_HD static int backward_pass(const SolveParams<S> &P, const TrajPtrs<S> &tr, const S *F, const S *Cfd, S *gterm, S lam,
+                                   S &dV0, S &dV1, bool &complete, unsigned mask, bool enabled) {
     const int T = P.T;
+    /* every lane of `mask` walks all T timesteps and meets the others at the top of each; a lane that is not
+     * `enabled` (its trajectory needs no further pass) or whose boxQP has failed skips the bodies */
+    int failed_at = enabled ? -1 : T;
     const S *mp = P.mp;
     S Va[N][NA]; /* [Vxx | Vx] at i+1, then at i */
     {            /* Vx[T] = cx[T], Vxx[T] = cxx[T]  (:353-354) */
@@ -212,6 +239,8 @@ struct Phases {
     load_run<N>(xn, tr.xs + (size_t)(T - 1) * N);
     load_run<M>(un, tr.us + (size_t)(T - 1) * M);
     for (int t = T - 1; t >= 0; t--) {
+      reconverge(mask);
+      if (failed_at >= 0) continue;
       S Fm[NM * N], xt[N], ut[M]; /* Fm[c * N + q]: column c of [fx | fu] */
 #pragma unroll
       for (int e = 0; e < NM * N; e++) Fm[e] = Fn[e];
@@ -267,7 +296,10 @@ struct Phases {
       if constexpr (M == 1) {
         const S Quu = Q[N][N], Qu = Qv[N];
         const QPScalar<S> r = box_qp_scalar<S>(P.qp, QuuF[0], Qu, kprev[0], P.u_min[0] - ut[0], P.u_max[0] - ut[0]);
-        if (r.result < 1) return t; /* :371 */
+        if (r.result < 1) { /* :371 */
+          failed_at = t;
+          continue;
+        }
         const S kk = r.x;
         const S nH = -r.Hinv;
         const bool fr = r.v_free != 0;
@@ -279,6 +311,7 @@ struct Phases {
         for (int b = 0; b < N; b++) Kg[b] = fr ? nH * Q[N][b] : S(0);
         store_run<N>(tr.K + (size_t)t * N, Kg); /* :396-397 */
         tr.k[t] = kk;
+        gterm[t] = CoreT::gn_term(&kk, ut); /* :405-412, summed in ascending order after the pass */
 #pragma unroll
         for (int a = 0; a < N; a++) {
           const S qa = Q[N][a];
@@ -303,7 +336,10 @@ struct Phases {
           w.hi[j] = P.u_max[j] - ut[j];
         }
         box_qp_generic<M, S>(P.qp, w);
-        if (w.result < 1) return t;
+        if (w.result < 1) {
+          failed_at = t;
+          continue;
+        }
         S Ka[M][NA]; /* [K | k] */
 #pragma unroll
         for (int j = 0; j < M; j++)
@@ -362,6 +398,7 @@ struct Phases {
           tr.k[(size_t)t * M + j] = Ka[j][N];
           store_run<N>(tr.K + ((size_t)t * M + j) * N, Ka[j]);
         }
+        gterm[t] = CoreT::gn_term(kprev, ut);
         /* [Vxx | Vx] (:391-392) */
         S ktq[N][M]; /* row aa of K^T Quu */
 #pragma unroll
@@ -393,6 +430,9 @@ struct Phases {
 #pragma unroll
         for (int b = 0; b < NA; b++) Va[a][b] = S(0.5) * (Vt[a][b] + (b < N ? Vt[b < N ? b : 0][a] : Vt[a][b]));
     }
+    reconverge(mask);
+    complete = failed_at < 0; /* a failure at timestep 0 returns 0 like a success (:371 vs :142) but is not complete */
+    if (failed_at >= 0) return failed_at < T ? failed_at : 0;
     /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
 #pragma unroll
     for (int r = 0; r < N; r++) {
@@ -406,40 +446,69 @@ struct Phases {
   /* get_gradient_norm (:405-412): mean_t max_j |k_tj| / (|u_tj| + 1), ascending t, from k and us in global memory.
    * After a pass that stopped at timestep d the entries at and below d are the previous pass's, as in the
    * reference (its k is only overwritten down to the failing step). */
+  /* the same from the terms a COMPLETE pass left in gterm (same operands, same operations as gn_term on k / us) */
+  ILQR_HD static S gradient_norm_terms(const SolveParams<S> &P, const S *gterm) {
+    const int T = P.T;
+    S acc = 0;
+    int t = 0;
+    for (; t + 4 <= T; t += 4) {
+      S g[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) g[q] = gterm[t + q];
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc += g[q];
+    }
+    for (; t < T; t++) acc += gterm[t];
+    return acc / T;
+  }
   ILQR_HD static S gradient_norm(const SolveParams<S> &P, const TrajPtrs<S> &tr) {
     const int T = P.T;
     S acc = 0;
-    for (int t = 0; t < T; t++) acc += CoreT::gn_term(tr.k + (size_t)t * M, tr.us + (size_t)t * M);
+    int t = 0;
+    for (; t + 4 <= T; t += 4) { /* four timesteps' loads and divisions in flight; the sum stays in ascending order */
+      S g[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) g[q] = CoreT::gn_term(tr.k + (size_t)(t + q) * M, tr.us + (size_t)(t + q) * M);
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc += g[q];
+    }
+    for (; t < T; t++) acc += CoreT::gn_term(tr.k + (size_t)t * M, tr.us + (size_t)t * M);
     return acc / T;
   }
 
   /* The head of a loop trip for one running trajectory (:115-159): bookkeeping of the derivative refresh (done by
    * the sweep phase just before), backward pass with the lambda retries, gradient-norm exit.  Leaves in s.roll what
    * the line search has to do.  s lives in registers / local memory; the caller stores it back. */
-  ILQR_HD static void backward_trip(const SolveParams<S> &P, const TrajPtrs<S> &tr, const S *F, const S *Cfd, TrajState<S> &s) {
+  ILQR_HD static void backward_trip(const SolveParams<S> &P, const TrajPtrs<S> &tr, const S *F, const S *Cfd, S *gterm,
+                                    TrajState<S> &s, unsigned mask) {
     s.trips++;
     if (s.flg_change) {
       s.flg_change = 0;
       s.n_deriv++;
     }
-    bool back_done = false;
-    for (;;) { /* :136-150 */
-      S dV0, dV1;
+    bool back_done = false, need = true, complete = false;
+    while (lanes_any(mask, need)) { /* :136-150; the lanes of a warp pass through together (see reconverge) */
+      S dV0 = 0, dV1 = 0;
+      bool done_all = false;
+      const int diverge = backward_pass(P, tr, F, Cfd, gterm, s.lam, dV0, dV1, done_all, mask, need);
+      if (!need) continue;
+      complete = done_all;
       s.n_backward++;
-      const int diverge = backward_pass(P, tr, F, Cfd, s.lam, dV0, dV1);
       s.dV0 = dV0;
       s.dV1 = dV1;
       s.diverge = diverge;
       if (diverge != 0) {
         s.dlam = CoreT::fmax_(s.dlam * P.lambda_factor, P.lambda_factor);
         s.lam = CoreT::fmax_(s.lam * s.dlam, P.lambda_min);
-        if (s.lam > P.lambda_max) break;
+        if (s.lam > P.lambda_max) need = false;
         continue;
       }
       back_done = true;
-      break;
+      need = false;
     }
-    s.gnorm = gradient_norm(P, tr);
+    /* a pass that stopped early (or at timestep 0, which the reference cannot tell from success) left stale entries:
+     * then the norm is formed from k and us as they stand, like the reference's */
+    s.gnorm = (back_done && complete) ? gradient_norm_terms(P, gterm) : gradient_norm(P, tr);
     if (s.gnorm < P.tol_grad && s.lam < P.grad_lambda_gate) { /* :153-159: `break` before iter++ */
       s.status = kExitGrad;
       s.roll = kRollStop;
@@ -647,14 +716,441 @@ __global__ void __launch_bounds__(kBackwardThreads) phase_backward_kernel(const 
   const int n_act = a.buf.n_act[a.parity];
   const int i = blockIdx.x * kBackwardThreads + threadIdx.x;
   if (i == 0) a.buf.n_act[a.parity ^ 1] = 0; /* the list this trip's accept phase fills */
+  const unsigned mask = __ballot_sync(0xffffffffu, i < n_act);
   if (i >= n_act) return;
   const long long b = a.buf.act[(size_t)a.parity * a.B + i];
   const TrajPtrs<S> tr = phase_pointers(a, b, N, M);
   const S *F = a.buf.F + b * (size_t)a.P.T * NM * N;
   const S *Cfd = CD == kCostFD ? a.buf.C + b * (size_t)a.P.T * Ph::NCF : nullptr;
   TrajState<S> s = *tr.st;
-  Ph::backward_trip(a.P, tr, F, Cfd, s);
+  Ph::backward_trip(a.P, tr, F, Cfd, a.buf.gterm + b * (size_t)a.P.T, s, mask);
   *tr.st = s;
+}
+
+/* Model::cost_d1 / cost_d2 for a row index known only at run time (the row a lane owns): the models' functions take
+ * the index as a plain argument, so this is just a call; kept as a named hook for models that specialise it. */
+template <class Model, typename S>
+__device__ __forceinline__ S cost_d1_rt(int c, const S *x, const S *u, const S *mp) { return Model::cost_d1(c, x, u, mp, false); }
+template <class Model, typename S>
+__device__ __forceinline__ S cost_d2_rt(int c, int d, const S *x, const S *u, const S *mp) { return Model::cost_d2(c, d, x, u, mp, false); }
+
+/* The backward phase for MID-SIZED active sets: kRowLanes = 8 lanes per trajectory, lane c owning ROW c of the stacked
+ * variable (x | u) for the whole pass.  With its row of F and a copy of [Vxx' | Vx'] a lane forms its row of
+ * W = F^T [Vxx' | Vx'] and then its row of the Q-function entirely in registers (no exchange between the two
+ * products); the lane of the first control row runs the boxQP on its own entries and publishes [K | k] and the
+ * control rows of Q; the state-row lanes then form their rows of the value function, swap the off-diagonal entries
+ * through shared memory for the symmetrisation, and publish the new [Vxx | Vx].  Three warp barriers per timestep,
+ * ~50 scalars of shared memory per trajectory, four trajectories per warp advancing in lockstep.  The chain per timestep is a quarter of
+ * the one-thread-per-trajectory kernel's and the instruction count per trajectory a fifth of the 32-lane
+ * decomposition's, which is what a batch of a few thousand trajectories (BASELINE configs[1]) needs: too few to
+ * fill the machine one thread each, too many to give each a warp.  Same expressions, same bits. */
+constexpr int kRowLanes = 8;
+constexpr int kRowThreads = 128;
+template <class Model, typename S, int CD>
+struct RowScratch {
+  static constexpr int N = Model::N, M = Model::M, NM = N + M, NA = N + 1, NCF = NM + NM * NM;
+  alignas(16) S Va[N * NA];        /* [Vxx | Vx] of the step above */
+  alignas(16) S Vt[N * N];         /* unsymmetrised Vxx of this step, for the transposed read */
+  alignas(16) S Uq[M * (NM + 1)];  /* the control rows of the Q-function: [Qux | Quu | Qu] */
+  alignas(16) S Kk[M * NA];        /* [K | k] */
+  S Cf[NCF];                       /* terminal cost derivatives, full layout */
+  S QuuF[M * M];                   /* regularised Quu */
+  S lam;
+  int fail; /* failing timestep of the current pass, or -1 */
+  int need; /* another pass is wanted (lambda retry, :142-148) */
+};
+
+/* GPW = trajectories (lane groups) per warp: 4 fills the lanes; fewer leaves lanes idle but serialises fewer boxQP
+ * lanes per warp and spreads a small active set over more schedulers */
+template <class Model, typename S, int CD, int GPW>
+__global__ void __launch_bounds__(kRowThreads, 2) phase_backward_rows_kernel(const __grid_constant__ PArgs<S> a) {
+  using Ph = Phases<Model, S, CD>;
+  using CoreT = typename Ph::CoreT;
+  constexpr int N = Model::N, M = Model::M, NM = N + M, NA = N + 1, NCF = NM + NM * NM, G = kRowLanes;
+  static_assert(NM <= G, "one row of the stacked variable per lane");
+  constexpr int kPerCta = (kRowThreads / 32) * GPW;
+  __shared__ RowScratch<Model, S, CD> scr[kPerCta];
+  const int wl = threadIdx.x & 31;
+  const int grp = (threadIdx.x >> 5) * GPW + wl / G, lane = wl % G;
+  const int n_act = a.buf.n_act[a.parity];
+  const int i = (wl / G < GPW) ? blockIdx.x * kPerCta + grp : 0x7fffffff;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.buf.n_act[a.parity ^ 1] = 0; /* the list this trip's accept phase fills */
+  /* The four trajectories of a warp advance in lockstep: every barrier below is warp-wide (over the lanes that carry a
+   * trajectory), so the row products and the value update of the four groups issue as ONE instruction stream with
+   * 4 x (n + m) lanes active, and only the boxQP lanes ever run apart.  (With group-wide barriers the groups drifted
+   * and the warp issued four streams in turn: ncu 15 threads per instruction, 3.6 k cycles per timestep.) */
+  const unsigned gmask = __ballot_sync(0xffffffffu, i < n_act);
+  if (i >= n_act) return;
+  const long long b = a.buf.act[(size_t)a.parity * a.B + i];
+  const TrajPtrs<S> tr = phase_pointers(a, b, N, M);
+  const SolveParams<S> &P = a.P;
+  const int T = P.T;
+  const S *mp = P.mp;
+  const S *F = a.buf.F + b * (size_t)T * NM * N;
+  const S *Cfd = CD == kCostFD ? a.buf.C + b * (size_t)T * NCF : nullptr;
+  RowScratch<Model, S, CD> &sc = scr[grp];
+  S *gterm = a.buf.gterm + b * (size_t)T;
+  const bool qp_lane = lane == N; /* first control row: boxQP, scalars, state record */
+  const int c = lane < NM ? lane : 0; /* this lane's row (lanes >= n + m idle along on row 0 and store nothing) */
+  const bool has_row = lane < NM;
+  TrajState<S> s;
+  if (qp_lane) {
+    s = *tr.st;
+    s.trips++;
+    if (s.flg_change) {
+      s.flg_change = 0;
+      s.n_deriv++;
+    }
+    sc.lam = s.lam;
+    sc.need = 1;
+  }
+  bool back_done = false, complete = false;
+  __syncwarp(gmask);
+  while (__any_sync(gmask, sc.need != 0)) { /* :136-150; a group that needs no further pass idles through it */
+    const bool enabled = sc.need != 0;
+    const S lam = sc.lam;
+    /* Vx[T] = cx[T], Vxx[T] = cxx[T]  (:353-354) */
+    {
+      S xT[N], uz[M];
+      load_run<N>(xT, tr.xs + (size_t)T * N);
+#pragma unroll
+      for (int j = 0; j < M; j++) uz[j] = 0;
+      if constexpr (CD == kCostFD) {
+        for (int o = lane; o < CoreT::kStencilTerm; o += G) CoreT::cost_stencil_s(P, o, true, xT, uz, sc.Cf);
+      } else {
+        if (lane == 0) CoreT::analytic_cost_s(P, xT, uz, true, sc.Cf);
+      }
+    }
+    __syncwarp(gmask);
+    for (int e = lane; e < N * NA; e += G) {
+      const int r = e / NA, bb = e % NA;
+      sc.Va[e] = (bb < N) ? sc.Cf[CoreT::ix_cxx(r, bb < N ? bb : 0)] : sc.Cf[r];
+    }
+    if (qp_lane) sc.fail = enabled ? -1 : T;
+    S kprev[M]; /* :369 warm start of i = T-1: the previous pass's k[T-1] */
+#pragma unroll
+    for (int j = 0; j < M; j++) kprev[j] = tr.k[(size_t)(T - 1) * M + j];
+    S dV0 = 0, dV1 = 0; /* :356 */
+    S Vrow[NA];         /* this lane's row of [Vxx | Vx] after the last step */
+#pragma unroll
+    for (int e = 0; e < NA; e++) Vrow[e] = 0;
+    S Fn[NM * N], xn[N], un[M];
+    load_run<NM * N>(Fn, F + (size_t)(T - 1) * NM * N);
+    load_run<N>(xn, tr.xs + (size_t)(T - 1) * N);
+    load_run<M>(un, tr.us + (size_t)(T - 1) * M);
+    __syncwarp(gmask);
+    for (int t = T - 1; t >= 0; t--) {
+      const bool live = sc.fail < 0; /* uniform in the group: written before a barrier every lane has passed */
+      S Fm[NM * N], xt[N], ut[M];
+#pragma unroll
+      for (int e = 0; e < NM * N; e++) Fm[e] = Fn[e];
+#pragma unroll
+      for (int e = 0; e < N; e++) xt[e] = xn[e];
+#pragma unroll
+      for (int e = 0; e < M; e++) ut[e] = un[e];
+      if (t > 0 && live) {
+        load_run<NM * N>(Fn, F + (size_t)(t - 1) * NM * N);
+        load_run<N>(xn, tr.xs + (size_t)(t - 1) * N);
+        load_run<M>(un, tr.us + (size_t)(t - 1) * M);
+      }
+      S cvec = 0, crow[NM]; /* this row's finite-difference cost derivatives */
+      if constexpr (CD == kCostFD) {
+        cvec = Cfd[(size_t)t * NCF + c];
+#pragma unroll
+        for (int d = 0; d < NM; d++) crow[d] = Cfd[(size_t)t * NCF + NM + c * NM + d];
+      }
+      S Va[N][NA];
+#pragma unroll
+      for (int q = 0; q < N; q++) load_run<NA>(Va[q], sc.Va + q * NA);
+      /* this lane's row of F (selected once: c is fixed for the kernel, the select chain is cheap next to the products) */
+      S Fc[N];
+#pragma unroll
+      for (int q = 0; q < N; q++) {
+        S v = Fm[q];
+#pragma unroll
+        for (int cc = 1; cc < NM; cc++) v = (c == cc) ? Fm[cc * N + q] : v;
+        Fc[q] = v;
+      }
+      /* row c of W = F^T [Vxx' | Vx'] and of the Q-function (:359-367) */
+      S W[N], Qv, Q[NM];
+#pragma unroll
+      for (int bb = 0; bb < NA; bb++) {
+        S w = Fc[0] * Va[0][bb];
+#pragma unroll
+        for (int q = 1; q < N; q++) w = w + Fc[q] * Va[q][bb];
+        if (bb < N) W[bb < N ? bb : 0] = w;
+        else {
+          S c1;
+          if constexpr (CD == kCostFD) c1 = cvec;
+          else c1 = cost_d1_rt<Model, S>(c, xt, ut, mp);
+          Qv = c1 + w;
+        }
+      }
+      S QuuFrow[M];
+#pragma unroll
+      for (int d = 0; d < NM; d++) {
+        S acc = W[0] * Fm[d * N];
+#pragma unroll
+        for (int r = 1; r < N; r++) acc = acc + W[r] * Fm[d * N + r];
+        S cc;
+        if constexpr (CD == kCostFD) cc = crow[d];
+        else cc = cost_d2_rt<Model, S>(c, d, xt, ut, mp);
+        Q[d] = cc + acc;
+        if (d >= N) QuuFrow[d - N] = (cc + (c == d ? lam : S(0))) + acc;
+      }
+      /* the control rows go to shared memory; with one control its lane solves the QP on its own registers first */
+      if (live && has_row && c >= N) {
+        const int j = c - N;
+#pragma unroll
+        for (int d = 0; d < NM; d++) sc.Uq[j * (NM + 1) + d] = Q[d];
+        sc.Uq[j * (NM + 1) + NM] = Qv;
+#pragma unroll
+        for (int d = 0; d < M; d++) sc.QuuF[j * M + d] = QuuFrow[d];
+      }
+      if constexpr (M == 1) {
+        /* The QP's three inputs go from the control row's lane to every lane of its group, and every lane solves it
+         * (same instructions on the same operands; the warm start kprev is tracked by every lane): the four groups of
+         * the warp then run the common path of the solver as one instruction stream instead of four lone lanes. */
+        const int src = (wl & ~(G - 1)) + N;
+        const S QuuF_b = __shfl_sync(gmask, QuuFrow[0], src);
+        const S Qu_b = __shfl_sync(gmask, Qv, src);
+        QPScalar<S> r;
+        r.result = 1;
+        r.x = 0;
+        r.Hinv = 0;
+        r.v_free = 0;
+        if (live) r = box_qp_scalar<S>(P.qp, QuuF_b, Qu_b, kprev[0], P.u_min[0] - ut[0], P.u_max[0] - ut[0]);
+        if (live && r.result >= 1) kprev[0] = r.x;
+        if (live && qp_lane) {
+          const S Quu = Q[N], Qu = Qv;
+          if (r.result < 1) {
+            sc.fail = t; /* :371 */
+          } else {
+            const S kk = r.x;
+            const S nH = -r.Hinv;
+            const bool fr = r.v_free != 0;
+            dV0 += kk * Qu;                    /* :388 */
+            dV1 += ((S(0.5) * kk) * Quu) * kk; /* :389, unregularised Quu */
+            gterm[t] = CoreT::gn_term(&kk, ut);
+            S Kg[NA];
+#pragma unroll
+            for (int bb = 0; bb < N; bb++) Kg[bb] = fr ? nH * Q[bb] : S(0);
+            Kg[N] = kk;
+#pragma unroll
+            for (int bb = 0; bb < NA; bb++) sc.Kk[bb] = Kg[bb];
+            store_run<N>(tr.K + (size_t)t * N, Kg); /* :396-397 */
+            tr.k[t] = kk;
+          }
+        }
+      } else {
+        __syncwarp(gmask);
+        if (live && qp_lane) {
+          QPWork<M, S> w;
+#pragma unroll
+          for (int e = 0; e < M * M; e++) w.Q[e] = sc.QuuF[e];
+#pragma unroll
+          for (int j = 0; j < M; j++) {
+            w.c[j] = sc.Uq[j * (NM + 1) + NM];
+            w.x0[j] = kprev[j];
+            w.lo[j] = P.u_min[j] - ut[j];
+            w.hi[j] = P.u_max[j] - ut[j];
+          }
+          box_qp_generic<M, S>(P.qp, w);
+          if (w.result < 1) {
+            sc.fail = t;
+          } else {
+            S Ka[M][NA];
+#pragma unroll
+            for (int j = 0; j < M; j++)
+#pragma unroll
+              for (int bb = 0; bb < NA; bb++) Ka[j][bb] = 0;
+#pragma unroll
+            for (int j = 0; j < M; j++) Ka[j][N] = w.x[j];
+            const int rd = w.r_dim;
+            int nf = 0;
+            for (int j = 0; j < M; j++)
+              if (w.v_free[j]) w.idx[nf++] = j;
+            if (nf > 0) { /* K on the free dimensions: -R^-1 R^-T Qux[free] (:376-385) */
+              for (int aa = 0; aa < rd && aa < nf; aa++)
+                for (int bb = 0; bb < N; bb++) {
+                  S acc = 0;
+                  for (int cc = 0; cc < rd && cc < nf; cc++) acc += (-w.Hinv[aa * rd + cc]) * sc.Uq[w.idx[cc] * (NM + 1) + bb];
+#pragma unroll
+                  for (int j = 0; j < M; j++)
+                    if (w.idx[aa] == j) Ka[j][bb] = acc;
+                }
+            }
+            {
+              Acc<S> a0; /* :388-389, unregularised Quu */
+#pragma unroll
+              for (int j = 0; j < M; j++) a0.add(Ka[j][N] * sc.Uq[j * (NM + 1) + NM]);
+              dV0 += a0.v;
+              Acc<S> a1;
+              S row[M];
+#pragma unroll
+              for (int bb = 0; bb < M; bb++) {
+                Acc<S> acc;
+#pragma unroll
+                for (int aa = 0; aa < M; aa++) acc.add((S(0.5) * Ka[aa][N]) * sc.Uq[aa * (NM + 1) + N + bb]);
+                row[bb] = acc.v;
+              }
+#pragma unroll
+              for (int bb = 0; bb < M; bb++) a1.add(row[bb] * Ka[bb][N]);
+              dV1 += a1.v;
+            }
+#pragma unroll
+            for (int j = 0; j < M; j++) { /* :396-397, and the warm start of the next boxQP (:369) */
+              kprev[j] = Ka[j][N];
+              tr.k[(size_t)t * M + j] = Ka[j][N];
+              store_run<N>(tr.K + ((size_t)t * M + j) * N, Ka[j]);
+#pragma unroll
+              for (int bb = 0; bb < NA; bb++) sc.Kk[j * NA + bb] = Ka[j][bb];
+            }
+            gterm[t] = CoreT::gn_term(kprev, ut);
+          }
+        }
+      }
+      __syncwarp(gmask); /* S1: [K | k], the control rows of Q and the verdict of the QP are published */
+      const bool live2 = live && sc.fail < 0;
+      /* row a = c of the unsymmetrised value function (:391-392), by the state-row lanes */
+      S Vt[NA];
+      {
+        S Ka[M][NA], Uq[M][NM + 1];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          load_run<NA>(Ka[j], sc.Kk + j * NA);
+          load_run<NM + 1>(Uq[j], sc.Uq + j * (NM + 1));
+        }
+        S Kca[M], Uca[M]; /* K[.][a] and Qux[.][a] for this lane's a (a select chain: a is fixed for the kernel) */
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          S kv = Ka[j][0], uv = Uq[j][0];
+#pragma unroll
+          for (int q = 1; q < N; q++) {
+            kv = (c == q) ? Ka[j][q] : kv;
+            uv = (c == q) ? Uq[j][q] : uv;
+          }
+          Kca[j] = kv;
+          Uca[j] = uv;
+        }
+        S ktq[M]; /* row a of K^T Quu */
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          Acc<S> acc;
+#pragma unroll
+          for (int cc = 0; cc < M; cc++) acc.add(Kca[cc] * Uq[cc][N + j]);
+          ktq[j] = acc.v;
+        }
+#pragma unroll
+        for (int bb = 0; bb < NA; bb++) {
+          Acc<S> t1, t2, t3;
+#pragma unroll
+          for (int cc = 0; cc < M; cc++) t1.add(ktq[cc] * Ka[cc][bb]);
+#pragma unroll
+          for (int cc = 0; cc < M; cc++) t2.add(Kca[cc] * (bb < N ? Uq[cc][bb < N ? bb : 0] : Uq[cc][NM]));
+#pragma unroll
+          for (int cc = 0; cc < M; cc++) t3.add(Uca[cc] * Ka[cc][bb]);
+          Vt[bb] = (bb < N ? Q[bb < N ? bb : 0] : Qv) + t1.v + t2.v + t3.v;
+        }
+      }
+      if (live2 && lane < N) {
+#pragma unroll
+        for (int bb = 0; bb < N; bb++) sc.Vt[lane * N + bb] = Vt[bb];
+      }
+      __syncwarp(gmask); /* S2 */
+      if (live2 && lane < N) { /* the symmetrisation (:393); the Vx column is copied: 0.5 * (v + v) */
+#pragma unroll
+        for (int bb = 0; bb < NA; bb++) {
+          const S other = bb < N ? sc.Vt[(bb < N ? bb : 0) * N + lane] : Vt[bb];
+          Vrow[bb] = S(0.5) * (Vt[bb] + other);
+        }
+#pragma unroll
+        for (int bb = 0; bb < NA; bb++) sc.Va[lane * NA + bb] = Vrow[bb];
+      }
+      __syncwarp(gmask); /* S3: [Vxx | Vx] of this step is published */
+    }
+    const int failed_at = sc.fail;
+    if (enabled && failed_at < 0 && lane < N) { /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
+      tr.Vx0[lane] = Vrow[N];
+#pragma unroll
+      for (int bb = 0; bb < N; bb++) tr.Vxx0[lane * N + bb] = Vrow[bb];
+    }
+    __syncwarp(gmask); /* every lane has read sc.fail / sc.lam / sc.need before the QP lane rewrites them */
+    if (enabled && qp_lane) {
+      const int diverge = failed_at >= 0 ? failed_at : 0;
+      complete = failed_at < 0;
+      s.n_backward++;
+      s.dV0 = dV0;
+      s.dV1 = dV1;
+      s.diverge = diverge;
+      int need = 0;
+      if (diverge != 0) {
+        s.dlam = CoreT::fmax_(s.dlam * P.lambda_factor, P.lambda_factor);
+        s.lam = CoreT::fmax_(s.lam * s.dlam, P.lambda_min);
+        need = !(s.lam > P.lambda_max);
+      } else {
+        back_done = true;
+      }
+      sc.lam = s.lam;
+      sc.need = need;
+    }
+    __syncwarp(gmask);
+  }
+  if (qp_lane) {
+    __threadfence_block(); /* K / k were written by this lane; the reads below are its own */
+    s.gnorm = (back_done && complete) ? Ph::gradient_norm_terms(P, gterm) : Ph::gradient_norm(P, tr);
+    if (s.gnorm < P.tol_grad && s.lam < P.grad_lambda_gate) { /* :153-159 */
+      s.status = kExitGrad;
+      s.roll = kRollStop;
+    } else {
+      s.roll = back_done ? kRollGo : kRollSkip;
+    }
+    *tr.st = s;
+  }
+}
+
+/* The head of a trip for SMALL active sets: one warp per trajectory runs Core::trip_pre — derivative sweep (when the
+ * trajectory changed), backward pass, gradient test — exactly as the persistent warp kernel does (ilqr_kernel.cuh),
+ * against the trajectory's own F / C arrays.  One thread per trajectory (phase_backward_kernel) has the lowest cost
+ * per trajectory but the longest chain per timestep (one lane issues the whole step: ~3 us); with a few thousand
+ * trajectories in flight the machine is far from full and the 32-lane decomposition (~0.7 us per step) finishes the
+ * phase sooner.  Same arithmetic, same bits; the host picks per trip from the size of the active list. */
+template <class Model, typename S, int CD>
+__global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) phase_pre_warp_kernel(const __grid_constant__ PArgs<S> a) {
+  constexpr int N = Model::N, M = Model::M, NM = N + M;
+  using Ex = WarpExec<N, M, S, 32>;
+  using CoreT = Core<Model, S, CD, Ex>;
+  using Sc = typename CoreT::Sc;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t per_group = warp_smem_bytes<Sc, S>(a.P.T);
+  const int group = threadIdx.x >> 5;
+  unsigned char *mine = smem_raw + group * per_group;
+  Sc &sc = *reinterpret_cast<Sc *>(mine);
+  const int n_act = a.buf.n_act[a.parity];
+  const int i = blockIdx.x * kWarpsPerCta + group;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.buf.n_act[a.parity ^ 1] = 0; /* the list this trip's accept phase fills */
+  if (i >= n_act) return;
+  const long long b = a.buf.act[(size_t)a.parity * a.B + i];
+  const size_t T = (size_t)a.P.T;
+  SlotPtrs<S> sl;
+  sl.F = a.buf.F + b * T * NM * N;
+  sl.C = CD == kCostFD ? a.buf.C + b * T * Sc::NCF : nullptr;
+  sl.cand_x = nullptr;
+  sl.cand_u = nullptr;
+  sl.gterm = reinterpret_cast<S *>(mine + sizeof(Sc));
+  Ex ex;
+  ex.lane = threadIdx.x & 31;
+  ex.mask = 0xffffffffu;
+  ex.init_barrier(reinterpret_cast<unsigned long long *>(mine + per_group - 16));
+  CoreT core(a.P, sc, ex, phase_pointers(a, b, N, M), sl);
+  core.load_state();
+  core.trips_left = 1;
+  core.have_derivs = !a.force_sweep;
+  const int pre = core.trip_pre();
+  ex.lanes([&](int lane, typename CoreT::Lane &) {
+    if (lane == 0) sc.st.roll = pre == CoreT::kTripRoll ? kRollGo : (pre == CoreT::kTripNoRoll ? kRollSkip : kRollStop);
+  });
+  core.store_state();
 }
 
 constexpr int kRolloutThreads = 64;

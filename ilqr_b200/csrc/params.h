@@ -93,7 +93,15 @@ inline int make_solve_params(const ilqr_desc &d, SolveParams<S> *out) {
     P.u_max[j] = S(d.override_limits ? d.u_max[j] : hi[j]);
   }
   if (d.model_id == ILQR_MODEL_ACROBOT) {
-    P.mp[0] = S(3.1415); /* include/acrobot.h:20-21: the literal, not pi */
+    /* the goal of include/acrobot.h:20-21 (the literal 3.1415, not pi) unless the caller passes the goal of its own
+     * Acrobot object (the C++ host layer does, so an edited acrobot.h cannot silently diverge from the device) */
+    bool given = false;
+    for (int i = 0; i < 4; i++) given = given || d.model_params[i] != 0.0;
+    if (given) {
+      for (int i = 0; i < 4; i++) P.mp[i] = S(d.model_params[i]);
+    } else {
+      P.mp[0] = S(3.1415);
+    }
   } else if (d.model_id >= ILQR_MODEL_USER_BASE) {
     for (int i = 0; i < 16; i++) P.mp[i] = S(d.model_params[i]);
   } else {

@@ -1,6 +1,8 @@
 // batch_demo.cpp — the reference's models, unchanged, driving a batch through the host shim:
 //   batch_demo [B] [T]   -> solves B random acrobot instances (include/ilqr_synth.h, seed 12345) and prints
 //   per-instance cost / iterations for the first few, plus the single-trajectory API on instance 0.
+//   batch_demo B T PREFIX  additionally writes PREFIX.bin (whole batch, iLQR::export_batch) and PREFIX_b3.csv
+//   (trajectory 3 in the reference's CSV format).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -23,6 +25,10 @@ int main(int argc, char **argv) {
   solver.quiet = true;
   std::vector<double> cost = solver.solve_batch(X0, U0);
   for (int b = 0; b < B && b < 6; b++) printf("batch %d cost %.12f iterations %d\n", b, cost[b], solver.batch_iterations(b));
+  if (argc > 3) {
+    solver.export_batch(std::string(argv[3]) + ".bin");
+    solver.output_to_csv(std::string(argv[3]) + "_b3.csv", B > 3 ? 3 : 0);
+  }
   solver.generate_trajectory(X0[0], U0[0]);
   printf("single 0 cost %.12f iterations %d status %d xT %.9f %.9f %.9f %.9f\n", solver.get_cost(), solver.get_iterations(),
          solver.get_status(), solver.get_xs()[T](0), solver.get_xs()[T](1), solver.get_xs()[T](2), solver.get_xs()[T](3));

@@ -18,6 +18,8 @@
 #ifndef _ILQR_H_
 #define _ILQR_H_
 
+#include <stdio.h>
+
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -27,7 +29,10 @@
 #include "common.h"
 #include "model.h"
 
-struct ilqr_handle;
+#include "ilqr_b200.h"
+
+/* one trajectory (xs [T+1][n], us [T][m], row-major) in the reference's result format, src/ilqr_core.cpp:414-431 */
+void ilqr_write_csv(FILE *f, int T, int n, int m, const double *xs, const double *us);
 
 class iLQR {
  public:
@@ -40,7 +45,7 @@ class iLQR {
   void generate_trajectory();                                          /* continue the current solve      */
   void generate_trajectory(const VectorXd &x_0);                       /* warm start, src/ilqr_core.cpp:65-76 */
   void generate_trajectory(const VectorXd &x_0, const VecOfVecXd &u0); /* fresh solve, :59-62             */
-  void output_to_csv(const std::string filename);                      /* :414-431                        */
+  void output_to_csv(const std::string filename);                      /* :414-431, byte for byte          */
   double init_traj(const VectorXd &x_0, const VecOfVecXd &u_0);        /* :11-56, returns the initial cost */
 
   /* what the reference keeps private (include/ilqr.h:57-85) */
@@ -72,6 +77,11 @@ class iLQR {
   VecOfVecXd batch_xs(int b) const;
   VecOfVecXd batch_us(int b) const;
   int batch_iterations(int b) const { return batch_iters.at(b); }
+  int batch_exit_status(int b) const { return batch_status.at(b); }
+  /* results of the last solve_batch on disk: one trajectory in the reference's CSV format (what plot_results.py
+   * reads), or the whole batch in one binary file (layout in ilqr_host.cpp; reader: ilqr_b200/export.py) */
+  void output_to_csv(const std::string filename, int b) const;
+  void export_batch(const std::string filename) const;
 
   std::shared_ptr<Model> model;
   double dt;
@@ -80,11 +90,13 @@ class iLQR {
   int maxIter = 100;
   bool quiet = false; /* the reference prints a progress table; here only the banner lines survive */
   int cost_deriv = 0; /* ILQR_COST_FD (the reference's behaviour) | ILQR_COST_ANALYTIC */
+  int flags = 0;      /* ILQR_FLAG_* of include/ilqr_b200.h; 0 = the reference's behaviour */
 
  private:
   void create(long B, int T_);
   void fetch_single();
   ilqr_handle *h = nullptr;
+  ilqr_desc hdesc; /* what h was created with */
   long hB = 0;
   int hT = 0;
   int model_id = -1;
@@ -94,7 +106,8 @@ class iLQR {
   double cost_s = 0;
   int iterations = 0, status = 0;
   std::vector<double> bxs, bus;
-  std::vector<int> batch_iters;
+  std::vector<int> batch_iters, batch_status;
+  std::vector<double> batch_cost;
 };
 
 #endif

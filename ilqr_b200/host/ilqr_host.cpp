@@ -1,8 +1,11 @@
 // ilqr_host.cpp — `class iLQR` of ilqr_b200/host/ilqr.h on top of the C ABI (include/ilqr_b200.h).
 // Host orchestration only: marshal Eigen containers to the ABI's row-major arrays, call the library,
 // marshal back.  No solver arithmetic happens here.
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+
+#include <iostream>
 
 #include <random>
 #include <typeinfo>
@@ -148,9 +151,6 @@ void iLQR::register_device_twin(const std::type_info &type, const char *struct_n
 iLQR::~iLQR() { ilqr_destroy(h); }
 
 void iLQR::create(long B, int T_) {
-  if (h && hB == B && hT == T_) return;
-  ilqr_destroy(h);
-  h = nullptr;
   ilqr_desc d;
   memset(&d, 0, sizeof(d));
   d.model_id = model_id;
@@ -168,7 +168,14 @@ void iLQR::create(long B, int T_) {
   for (int i = 0; i < 16; i++) d.model_params[i] = model_params[i];
   ilqr_default_params(&d.params);
   d.params.max_iter = maxIter;
+  d.flags = flags;
+  // everything the handle was created with is in the descriptor: a changed limit (the reference reads model->u_min /
+  // u_max on every backward pass, src/ilqr_core.cpp:369), maxIter, cost_deriv or flag makes a new handle
+  if (h && memcmp(&d, &hdesc, sizeof(d)) == 0) return;
+  ilqr_destroy(h);
+  h = nullptr;
   check(ilqr_create(&d, &h), nullptr, "ilqr_create");
+  hdesc = d;
   hB = B;
   hT = T_;
 }
@@ -230,6 +237,9 @@ void iLQR::generate_trajectory(const VectorXd &x_0) {
 
 void iLQR::generate_trajectory() {
   if (!h) throw std::runtime_error("iLQR::generate_trajectory(): call init_traj first");
+  // every call re-enters the loop with iter = 0 and fresh derivatives, like the reference (src/ilqr_core.cpp:88-102);
+  // after init_traj / a warm start this changes nothing
+  check(ilqr_resume(h), h, "ilqr_resume");
   check(ilqr_solve(h), h, "ilqr_solve");
   fetch_single();
   if (!quiet) {
@@ -239,22 +249,68 @@ void iLQR::generate_trajectory() {
   output_to_csv("ilqr_result.csv");  // the reference does this at the end of every solve (src/ilqr_core.cpp:300)
 }
 
-// src/ilqr_core.cpp:414-431: header "x1, ..., xn, u0, ..., um" (the reference names one control column too many,
-// :418-419, kept), one %f row per knot, the last row states only.
+// src/ilqr_core.cpp:414-431, byte for byte: header "x1, ..., xn, u0, ..., um" (the reference names one control column
+// too many, :418-419), one row per knot with the last control written "%f\n" (:421-425), and the terminal row —
+// states only — ending in ", " with NO newline (:427); plot_results.py:15 tells the terminal row by that blank.
+void ilqr_write_csv(FILE *f, int T, int n, int m, const double *xs, const double *us) {
+  for (int i = 1; i <= n; i++) fprintf(f, "x%d, ", i);
+  for (int j = 0; j < m; j++) fprintf(f, "u%d, ", j);
+  fprintf(f, "u%d\n", m);
+  for (int t = 0; t < T; t++) {
+    for (int i = 0; i < n; i++) fprintf(f, "%f, ", xs[(size_t)t * n + i]);
+    for (int j = 0; j + 1 < m; j++) fprintf(f, "%f, ", us[(size_t)t * m + j]);
+    fprintf(f, "%f\n", us[(size_t)t * m + m - 1]);
+  }
+  for (int i = 0; i < n; i++) fprintf(f, "%f, ", xs[(size_t)T * n + i]);
+}
+
 void iLQR::output_to_csv(const std::string filename) {
   FILE *f = fopen(filename.c_str(), "w");
   if (!f) return;
   const int n = model->x_dims, m = model->u_dims;
-  for (int i = 0; i < n; i++) fprintf(f, "x%d, ", i + 1);
-  for (int j = 0; j <= m; j++) fprintf(f, j < m ? "u%d, " : "u%d", j);
-  fprintf(f, "\n");
-  for (int t = 0; t <= T; t++) {
-    for (int i = 0; i < n; i++) fprintf(f, "%f, ", xs[t](i));
-    if (t < T)
-      for (int j = 0; j < m; j++) fprintf(f, "%f, ", us[t](j));
-    fprintf(f, "\n");
-  }
+  std::vector<double> bx((size_t)(T + 1) * n), bu((size_t)T * m);
+  for (int t = 0; t <= T; t++)
+    for (int i = 0; i < n; i++) bx[(size_t)t * n + i] = xs[t](i);
+  for (int t = 0; t < T; t++)
+    for (int j = 0; j < m; j++) bu[(size_t)t * m + j] = us[t](j);
+  ilqr_write_csv(f, T, n, m, bx.data(), bu.data());
   fclose(f);
+  if (!quiet) std::cout << "Saved iLQR result to " << filename << std::endl;  // :430
+}
+
+// One trajectory of the last solve_batch in the reference's CSV format.
+void iLQR::output_to_csv(const std::string filename, int b) const {
+  const int n = model->x_dims, m = model->u_dims;
+  if (b < 0 || (size_t)(b + 1) * (T + 1) * n > bxs.size()) throw std::runtime_error("iLQR::output_to_csv: no such batch entry");
+  FILE *f = fopen(filename.c_str(), "w");
+  if (!f) return;
+  ilqr_write_csv(f, T, n, m, bxs.data() + (size_t)b * (T + 1) * n, bus.data() + (size_t)b * T * m);
+  fclose(f);
+}
+
+// The whole batch in one binary file (little endian): a 64-byte header
+//   char magic[8] = "ILQRB200"; uint32 version = 1, dtype (0 = f64), n, m, T, reserved; uint64 B; 24 bytes of zeros
+// then xs [B][T+1][n], us [B][T][m], cost [B] as f64 and iterations [B], status [B] as int32 — the ABI's own layouts,
+// so the file is what ilqr_get returned.  ilqr_b200/export.py reads it.
+void iLQR::export_batch(const std::string filename) const {
+  const int n = model->x_dims, m = model->u_dims;
+  const uint64_t B = batch_cost.size();
+  if (B == 0) throw std::runtime_error("iLQR::export_batch: no batch has been solved");
+  FILE *f = fopen(filename.c_str(), "wb");
+  if (!f) throw std::runtime_error("iLQR::export_batch: cannot open " + filename);
+  unsigned char head[64] = {0};
+  memcpy(head, "ILQRB200", 8);
+  const uint32_t w[6] = {1u, 0u, (uint32_t)n, (uint32_t)m, (uint32_t)T, 0u};
+  memcpy(head + 8, w, sizeof(w));
+  memcpy(head + 32, &B, sizeof(B));
+  bool ok = fwrite(head, 1, 64, f) == 64;
+  ok = ok && fwrite(bxs.data(), sizeof(double), bxs.size(), f) == bxs.size();
+  ok = ok && fwrite(bus.data(), sizeof(double), bus.size(), f) == bus.size();
+  ok = ok && fwrite(batch_cost.data(), sizeof(double), B, f) == B;
+  ok = ok && fwrite(batch_iters.data(), sizeof(int), B, f) == B;
+  ok = ok && fwrite(batch_status.data(), sizeof(int), B, f) == B;
+  fclose(f);
+  if (!ok) throw std::runtime_error("iLQR::export_batch: short write to " + filename);
 }
 
 std::vector<double> iLQR::solve_batch(const std::vector<VectorXd> &X0, const std::vector<VecOfVecXd> &U0) {
@@ -280,7 +336,11 @@ std::vector<double> iLQR::solve_batch(const std::vector<VectorXd> &X0, const std
   check(ilqr_get(h, ILQR_F_ITERS, iters.data(), 0), h, "ilqr_get");
   check(ilqr_get(h, ILQR_F_XS, bxs.data(), 0), h, "ilqr_get");
   check(ilqr_get(h, ILQR_F_US, bus.data(), 0), h, "ilqr_get");
+  std::vector<int32_t> stat(B);
+  check(ilqr_get(h, ILQR_F_STATUS, stat.data(), 0), h, "ilqr_get");
   batch_iters.assign(iters.begin(), iters.end());
+  batch_status.assign(stat.begin(), stat.end());
+  batch_cost = cost;
   return cost;
 }
 

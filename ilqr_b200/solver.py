@@ -85,8 +85,15 @@ class BatchILQR:
             self.set_initial(x0, u0)
         elif x0 is not None:
             self.warm_start(x0)
+        else:
+            self.resume()
         self.solve()
         return self
+
+    def resume(self):
+        """re-enter the loop like a second call of iLQR::generate_trajectory() (src/ilqr_core.cpp:78-102): loop counter 0,
+        derivatives refreshed, lambda / dlambda carried over"""
+        self._check(self.lib.ilqr_resume(self.h), "ilqr_resume")
 
     def warm_start(self, x0):
         x0 = self._host(x0, (self.B, self.n))
@@ -129,6 +136,17 @@ class BatchILQR:
             out = np.empty(self.field_shape(name), dtype=dt)
         self._check(self.lib.ilqr_get(self.h, fid, out.ctypes.data, 0), "ilqr_get(%s)" % name)
         return out
+
+    # -- result files (ilqr_b200/export.py) --------------------------------------------------------
+    def output_to_csv(self, filename, b=0):
+        """iLQR::output_to_csv (src/ilqr_core.cpp:414-431) for trajectory b of the batch, byte-compatible"""
+        from . import export
+        export.write_csv(filename, self.get("xs")[b], self.get("us")[b])
+
+    def export_batch(self, filename):
+        """the whole batch (xs, us, cost, iterations, status) in one binary file"""
+        from . import export
+        export.write_batch(filename, self.get("xs"), self.get("us"), self.get("cost"), self.get("iters"), self.get("status"))
 
     def get_device(self, name, dst_ptr):
         fid, _ = abi.FIELDS[name]

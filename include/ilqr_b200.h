@@ -106,7 +106,8 @@ typedef struct ilqr_desc {
   double dt;          /* iLQR(Model*, double timeDelta), include/ilqr.h:30 */
   double u_min[ILQR_MAX_M];
   double u_max[ILQR_MAX_M];
-  double model_params[16]; /* DOUBLE_INTEGRATOR: [0..3] goal state */
+  double model_params[16]; /* DOUBLE_INTEGRATOR: [0..3] goal state; ACROBOT: [0..3] goal state, all zero = the
+                              reference's (3.1415, 0, 0, 0) (acrobot.h:20-21); user models: passed through as `mp` */
   ilqr_params params;
 } ilqr_desc;
 
@@ -161,6 +162,11 @@ int ilqr_set_initial(ilqr_handle *h, const void *x0, const void *u0, int on_devi
 /* Warm start, iLQR::generate_trajectory(x_0) (src/ilqr_core.cpp:65-76): keep us, K, xs, and
  * lambda/dlambda of the previous solve, re-roll from a new x0[B][n] WITH feedback (:316). */
 int ilqr_warm_start(ilqr_handle *h, const void *x0, int on_device);
+
+/* "Continue", iLQR::generate_trajectory() called again (src/ilqr_core.cpp:78-102): every instance re-enters the loop
+ * with its counter at 0 and its derivatives refreshed, whatever its exit status was; lambda / dlambda carry over
+ * (include/ilqr.h:17-18).  Follow with ilqr_solve / ilqr_iterate. */
+int ilqr_resume(ilqr_handle *h);
 
 /* Up to n_iters more trips of the loop body (src/ilqr_core.cpp:103-288) per instance;
  * instances that have terminated stay as they are. */

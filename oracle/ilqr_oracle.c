@@ -822,6 +822,12 @@ orc_solver *orc_new(const ilqr_desc *desc) {
     s->n = 4; s->m = 1;
     s->umin[0] = -5; s->umax[0] = 5; /* acrobot.h:37 */
     s->goal[0] = 3.1415;              /* acrobot.h:20-21 */
+    {                                 /* ... unless the caller hands over the goal of its own Acrobot object */
+      int given = 0;
+      for (int i = 0; i < 4; i++) given = given || desc->model_params[i] != 0.0;
+      if (given)
+        for (int i = 0; i < 4; i++) s->goal[i] = desc->model_params[i];
+    }
   } else if (desc->model_id == ILQR_MODEL_DOUBLE_INTEGRATOR) {
     s->n = 4; s->m = 2;
     s->umin[0] = s->umin[1] = -0.5; s->umax[0] = s->umax[1] = 0.5; /* double_integrator.h:25-26 */
@@ -884,6 +890,14 @@ double orc_warm_start(orc_solver *s, const double *x0) {
   s->iter = 0;
   s->status = ILQR_RUNNING;
   return s->cost_s;
+}
+
+/* iLQR::generate_trajectory() called again on a finished solve (src/ilqr_core.cpp:78-102): the loop is re-entered
+ * with iter = 0 and flgChange = true; lambda / dlambda (TU statics, include/ilqr.h:17-18) carry over. */
+void orc_resume(orc_solver *s) {
+  s->flgChange = 1;
+  s->iter = 0;
+  s->status = ILQR_RUNNING;
 }
 
 int orc_iterate(orc_solver *s, int n_iters) { return iterate(s, n_iters); }

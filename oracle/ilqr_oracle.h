@@ -30,6 +30,7 @@ void orc_dims(const orc_solver *s, int *n, int *m);
 
 double orc_init(orc_solver *s, const double *x0, const double *u0, int T);
 double orc_warm_start(orc_solver *s, const double *x0);
+void orc_resume(orc_solver *s);
 int orc_iterate(orc_solver *s, int n_iters);
 int orc_backward_once(orc_solver *s, double lambda, int recompute_derivs);
 double orc_rollout_once(orc_solver *s, double alpha);

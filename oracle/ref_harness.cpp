@@ -227,6 +227,46 @@ class ILQRSetup_ForwardPassTest_Test {
     s->dlam = dlambda;
   }
 
+  // Warm start.  Replica of iLQR::generate_trajectory(const VectorXd&) up to the loop (src/ilqr_core.cpp:65-76):
+  // the same two statements on the reference's own members, then the loop-carried locals the reference
+  // re-initialises on entry to generate_trajectory() (:88-95, :102: flgChange = true, iter = 0).  lambda / dlambda are
+  // NOT touched: they are TU statics (include/ilqr.h:17-18) and carry over from the previous solve.
+  static double warm_start(RefState *s, const VectorXd &x_0) {
+    Silence quiet;
+    iLQR &q = *s->solver;
+    q.x0 = x_0;
+    const double cost_i = q.forward_pass(x_0, q.us);
+    q.cost_s = cost_i;
+    s->flgChange = true;
+    s->iter = 0;
+    s->status = REF_RUNNING;
+    return cost_i;
+  }
+  // The real warm start, start to finish: the TU statics are set to what this instance's previous solve left.
+  static void warm_native(RefState *s, const VectorXd &x_0) {
+    Silence quiet;
+    lambda = s->lam;
+    dlambda = s->dlam;
+    s->solver->generate_trajectory(x_0);
+    s->lam = lambda;
+    s->dlam = dlambda;
+  }
+  // "Continue": iLQR::generate_trajectory() called again on a finished solve re-enters the loop with iter = 0 and
+  // flgChange = true (:88-102), lambda / dlambda carried over.
+  static void resume(RefState *s) {
+    s->flgChange = true;
+    s->iter = 0;
+    s->status = REF_RUNNING;
+  }
+  static void resume_native(RefState *s) {
+    Silence quiet;
+    lambda = s->lam;
+    dlambda = s->dlam;
+    s->solver->generate_trajectory();
+    s->lam = lambda;
+    s->dlam = dlambda;
+  }
+
   static int T(RefState *s) { return s->solver->T; }
 
   // field ids shared with tests/refharness.py
@@ -350,6 +390,22 @@ void ref_solve_native(void *h, const double *x0, const double *u0, int T) {
   unpack(s, x0, u0, T, x, u);
   Probe::solve_native(s, x, u);
 }
+
+// generate_trajectory(x_0): replica entry (continue with ref_iterate) and the native call
+double ref_warm_start(void *h, const double *x0) {
+  RefState *s = (RefState *)h;
+  VectorXd x(s->n);
+  for (int i = 0; i < s->n; i++) x(i) = x0[i];
+  return Probe::warm_start(s, x);
+}
+void ref_warm_native(void *h, const double *x0) {
+  RefState *s = (RefState *)h;
+  VectorXd x(s->n);
+  for (int i = 0; i < s->n; i++) x(i) = x0[i];
+  Probe::warm_native(s, x);
+}
+void ref_resume(void *h) { Probe::resume((RefState *)h); }
+void ref_resume_native(void *h) { Probe::resume_native((RefState *)h); }
 
 int ref_get(void *h, int field, double *dst) { return Probe::get((RefState *)h, field, dst); }
 

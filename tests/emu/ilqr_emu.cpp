@@ -24,6 +24,7 @@ struct EmuBase {
   virtual double init(const double *x0, const double *u0, int T) = 0;
   virtual double warm_start(const double *x0) = 0;
   virtual void iterate(int n) = 0;
+  virtual void resume() = 0;
   virtual int backward_once(double lam) = 0;
   virtual double rollout_once(double alpha) = 0;
   virtual int get(int field, double *dst) = 0;
@@ -98,6 +99,11 @@ struct Emu : EmuBase {
     core().op_warm_start();
     return st.cost;
   }
+  void resume() override { /* ilqr_resume_kernel */
+    st.iter = 0;
+    st.flg_change = 1;
+    st.status = kRunning;
+  }
   void iterate(int cnt) override {
     if (phases) iterate_phases(cnt);
     else core().op_iterate(cnt);
@@ -120,7 +126,7 @@ struct Emu : EmuBase {
           for (int o = 0; o < Ph::kStencilStep; o++)
             for (int t = 0; t < T; t++) Ph::stencil_task(P, xs.data(), us.data(), bufC.data(), o, t);
       }
-      Ph::backward_trip(P, tr, bufF.data(), bufC.data(), st);
+      Ph::backward_trip(P, tr, bufF.data(), bufC.data(), gterm.data(), st, 1u);
       if (st.roll == kRollGo)
         for (int a = 0; a < na; a++) newcost[a] = Ph::rollout_task(P, tr, candX.data(), candU.data(), a);
       if (st.status != kRunning) break;
@@ -269,6 +275,7 @@ int emu_iterate(void *h, int n) {
   ((EmuBase *)h)->iterate(n);
   return 0;
 }
+void emu_resume(void *h) { ((EmuBase *)h)->resume(); }
 int emu_backward_once(void *h, double lam) { return ((EmuBase *)h)->backward_once(lam); }
 double emu_rollout_once(void *h, double alpha) { return ((EmuBase *)h)->rollout_once(alpha); }
 int emu_get(void *h, int field, double *dst) { return ((EmuBase *)h)->get(field, dst); }

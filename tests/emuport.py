@@ -100,6 +100,10 @@ class EmuSolver:
     def iterate(self, n):
         return self.L.emu_iterate(self.h, n)
 
+    def resume(self):
+        self.L.emu_resume.argtypes = [C.c_void_p]
+        self.L.emu_resume(self.h)
+
     def backward_once(self, lam=1.0):
         return self.L.emu_backward_once(self.h, lam)
 

@@ -99,6 +99,10 @@ class OracleSolver:
     def warm_start(self, x0):
         return lib().orc_warm_start(self.h, _p(_arr(x0)))
 
+    def resume(self):
+        lib().orc_resume.argtypes = [C.c_void_p]
+        lib().orc_resume(self.h)
+
     def iterate(self, n):
         return lib().orc_iterate(self.h, n)
 

@@ -116,6 +116,40 @@ class RefSolver:
             finally:
                 os.chdir(cwd)
 
+    def _in_tmp(self, fn):
+        cwd = os.getcwd()
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:  # generate_trajectory drops ilqr_result.csv in cwd
+            os.chdir(d)
+            try:
+                fn()
+            finally:
+                os.chdir(cwd)
+
+    def warm_start(self, x0):
+        """replica of generate_trajectory(x_0) up to the loop (src/ilqr_core.cpp:65-76); continue with iterate()"""
+        L = lib()
+        L.ref_warm_start.restype = C.c_double
+        L.ref_warm_start.argtypes = [C.c_void_p, _dp]
+        return L.ref_warm_start(self.h, _p(_arr(x0)))
+
+    def warm_native(self, x0):
+        """the reference's own generate_trajectory(x_0), start to finish"""
+        L = lib()
+        L.ref_warm_native.argtypes = [C.c_void_p, _dp]
+        x0 = _arr(x0)
+        self._in_tmp(lambda: L.ref_warm_native(self.h, _p(x0)))
+
+    def resume(self):
+        L = lib()
+        L.ref_resume.argtypes = [C.c_void_p]
+        L.ref_resume(self.h)
+
+    def resume_native(self):
+        L = lib()
+        L.ref_resume_native.argtypes = [C.c_void_p]
+        self._in_tmp(lambda: L.ref_resume_native(self.h))
+
     def get(self, name):
         T, n, m = self.T, self.n, self.m
         shapes = dict(xs=(T + 1, n), us=(T, m), K=(T, m, n), k=(T, m), cost=(1,), dV=(2,), Vx=(T + 1, n),

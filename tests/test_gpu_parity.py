@@ -231,9 +231,14 @@ ALL_FIELDS = ("xs", "us", "K", "k", "cost", "lambda", "dlambda", "dV", "gnorm", 
     (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_ANALYTIC, abi.F64, 99, 40, dict(goal=[0.5, -0.5, 0.0, 0.0])),
     (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_ANALYTIC, abi.F32, 60, 40, dict(goal=[1.0, 1.0, 0.0, 0.0])),
 ])
-def test_phase_engine_equals_warp_engine_bit_for_bit(model, cd, dtype, T, B, kw):
+@pytest.mark.parametrize("head", ["rows", "thread", "warp"])
+def test_phase_engine_equals_warp_engine_bit_for_bit(model, cd, dtype, T, B, kw, head, monkeypatch):
     """Both engines run the same arithmetic entry for entry (ilqr_phases.cuh uses Core's helpers), so every array,
     scalar and counter must agree BIT FOR BIT at every checkpoint up to termination, in every mode and dtype."""
+    # the head of a trip (sweep + backward) has three lane decompositions, picked by the size of the active set
+    # (ilqr_phase_launch.cuh); each is forced here in turn: 8 lanes per trajectory / 1 thread / 32 lanes
+    monkeypatch.setenv("ILQR_B200_ROWS_MAX", "0" if head == "thread" else "1000000")
+    monkeypatch.setenv("ILQR_B200_WARP_PRE_MAX", "1000000" if head == "warp" else "0")
     n, m = abi.MODEL_DIMS[model]
     x0, u0 = make_inputs(2024, B, T, n, m)
     dt = 0.02 if model == abi.MODEL_ACROBOT else 0.05
