@@ -102,7 +102,7 @@ EXPORTS = [
     "ilqr_default_params", "ilqr_model_info", "ilqr_create", "ilqr_destroy", "ilqr_last_error",
     "ilqr_set_initial", "ilqr_warm_start", "ilqr_resume", "ilqr_iterate", "ilqr_solve", "ilqr_backward_once",
     "ilqr_rollout_once", "ilqr_get", "ilqr_sync", "ilqr_stream", "ilqr_launch_count", "ilqr_make_inputs",
-    "ilqr_version", "ilqr_register_model", "ilqr_compile_model",
+    "ilqr_version", "ilqr_register_model", "ilqr_compile_model", "ilqr_measure_fp64",
 ]
 
 
@@ -139,6 +139,7 @@ def load():
     L.ilqr_make_inputs.argtypes = [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
                                    C.c_int, dp, dp]
     L.ilqr_version.restype = C.c_char_p
+    L.ilqr_measure_fp64.argtypes = [C.c_int32, dp, dp, dp]
     L.ilqr_register_model.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, dp, dp, ip]
     L.ilqr_compile_model.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t]
     _lib = L

@@ -73,6 +73,26 @@ __global__ void ilqr_resume_kernel(TrajState<S> *st, long long B) {
   st[b].status = kRunning;
 }
 
+/* fp64 issue-rate probe (ilqr_measure_fp64): 8 independent chains per thread, enough warps to fill every scheduler */
+template <int OP>
+__global__ void ilqr_fp64_probe_kernel(double a, double b, int n, double *sink) {
+  double x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = a + threadIdx.x + k;
+  for (int i = 0; i < n; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (OP == 0) x[k] = fma(x[k], b, a);
+      if (OP == 1) x[k] = x[k] * b;
+      if (OP == 2) x[k] = x[k] + b;
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += x[k];
+  if (s == 12345.678) sink[0] = s; /* never true: keeps the chains alive */
+}
+
 thread_local std::string g_create_error;
 
 }  // namespace
@@ -381,6 +401,46 @@ int ilqr_make_inputs(uint64_t seed, int64_t B, int32_t T, int32_t n, int32_t m, 
                      int canonical_first, double *x0, double *u0) {
   if (B < 0 || T < 1 || n < 1 || m < 1 || !x0 || !u0) return ILQR_E_INVALID;
   ilqr_synth_fill(seed, (size_t)B, T, n, m, x_scale, u_scale, canonical_first, x0, u0);
+  return ILQR_OK;
+}
+
+int ilqr_measure_fp64(int32_t device, double *fma_per_s, double *mul_per_s, double *add_per_s) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ILQR_E_CUDA;
+  DeviceGuard g(device);
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return ILQR_E_CUDA;
+  double *sink = nullptr;
+  if (cudaMalloc(&sink, 8) != cudaSuccess) return ILQR_E_NOMEM;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sms * 8, threads = 256, n = 1 << 15;
+  double out[3] = {0, 0, 0};
+  for (int op = 0; op < 3; op++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0);
+      if (op == 0) ilqr_fp64_probe_kernel<0><<<blocks, threads>>>(1.5, 1.0000001, n, sink);
+      if (op == 1) ilqr_fp64_probe_kernel<1><<<blocks, threads>>>(1.5, 1.0000001, n, sink);
+      if (op == 2) ilqr_fp64_probe_kernel<2><<<blocks, threads>>>(1.5, 1.0000001, n, sink);
+      cudaEventRecord(e1);
+      if (cudaEventSynchronize(e1) != cudaSuccess) {
+        cudaFree(sink);
+        return ILQR_E_CUDA;
+      }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+    }
+    out[op] = (double)blocks * threads * 8.0 * n / (best * 1e-3);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (fma_per_s) *fma_per_s = out[0];
+  if (mul_per_s) *mul_per_s = out[1];
+  if (add_per_s) *add_per_s = out[2];
   return ILQR_OK;
 }
 

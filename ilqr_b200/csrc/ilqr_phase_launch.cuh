@@ -14,7 +14,14 @@
 
 namespace ilqr {
 
-constexpr int kPhaseCheckEvery = 8; /* trips between read-backs of the active count */
+constexpr int kPhaseCheckEvery = 8; /* trips between read-backs of the active count (4 for small batches) */
+/* Running trajectories at or below which the lockstep rounds stop and the persistent warp-per-trajectory kernel
+ * finishes the solve.  A lockstep round costs its latency floor (~0.45 ms: the slowest trajectory's backward pass and
+ * rollout, one after the other) however few trajectories are left, and every trajectory waits for the slowest; the
+ * persistent kernel advances each survivor at its own pace (~0.25 ms per trip) once they all fit the machine at once
+ * (2368 resident warps).  Measured on BASELINE configs[1] (gpurun_out r2h/r2i): 59.7 ms lockstep only, 48.8 ms with
+ * the hand-over at 3200, 53.3 ms persistent kernel only. */
+constexpr long long kPhaseHandover = 3200;
 
 template <class Model, typename S, int CD>
 int phase_prepare(ilqr_handle *h) {
@@ -77,9 +84,9 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
   if (const char *e = getenv("ILQR_B200_ROWS_GPW")) rows_gpw = atoi(e);
   /* below this many running trajectories the lockstep rounds stop and the persistent warp-per-trajectory kernel
    * finishes the solve: every trajectory then advances at its own pace instead of the pace of the slowest */
-  long long handover = 0;
+  long long handover = kPhaseHandover;
   if (const char *e = getenv("ILQR_B200_HANDOVER")) handover = atoll(e);
-  int check_every = kPhaseCheckEvery;
+  int check_every = h->desc.B <= 16384 ? 4 : kPhaseCheckEvery;
   if (const char *e = getenv("ILQR_B200_CHECK_EVERY")) check_every = atoi(e) > 0 ? atoi(e) : check_every;
   constexpr int N = Model::N, M = Model::M;
   const size_t pre_smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S, 32>>::Sc, S>(h->desc.T) * kWarpsPerCta;

@@ -139,6 +139,23 @@ ILQR_HD_TRIG void sincos_det(double x, double *sn, double *cs) {
   /* tests/emu only: the platform libm, to compare the kernel source bit for bit with the oracle */
   *sn = ::sin(x);
   *cs = ::cos(x);
+#if defined(ILQR_TRIG_NOISE)
+  /* tools/exp_attribution.py only: "another correct libm" — a deterministic function of the argument that moves about
+   * one result in sixteen by one ulp, the kind of disagreement two < 1 ulp implementations have (trig.cuh and glibc
+   * disagree on 3 % of arguments, tests/test_trig.py) */
+  {
+    unsigned long long b;
+    __builtin_memcpy(&b, &x, 8);
+    b ^= b >> 29;
+    b *= 0x9E3779B97F4A7C15ULL;
+    b ^= b >> 32;
+    const unsigned h = (unsigned)(b & 63u);
+    if (h == 0) *sn = ::nextafter(*sn, 2.0);
+    if (h == 1) *sn = ::nextafter(*sn, -2.0);
+    if (h == 2) *cs = ::nextafter(*cs, 2.0);
+    if (h == 3) *cs = ::nextafter(*cs, -2.0);
+  }
+#endif
   return;
 #endif
   if (__builtin_expect(!sincos_in_range(x), 0)) {

@@ -194,6 +194,11 @@ int64_t ilqr_launch_count(const ilqr_handle *h);
 int ilqr_make_inputs(uint64_t seed, int64_t B, int32_t T, int32_t n, int32_t m, double x_scale, double u_scale,
                      int canonical_first, double *x0, double *u0);
 
+/* Measured fp64 issue rate of the device, in scalar operations per second (a fused multiply-add counts ONCE): the
+ * compute-side ceiling bench.py reports next to the HBM roofline (SURVEY.md §8d "secondary ceiling").  The library is
+ * built without FMA contraction, so its arithmetic runs at the mul / add rates. */
+int ilqr_measure_fp64(int32_t device, double *fma_per_s, double *mul_per_s, double *add_per_s);
+
 /* library build info: "ilqr_b200 <version> sm_100a ..." */
 const char *ilqr_version(void);
 

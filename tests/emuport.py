@@ -23,17 +23,25 @@ _ip = C.POINTER(C.c_int)
 _libs = {}
 
 
+LIB_PATH_NOISE = os.path.join(ROOT, "tests", "_build", "libilqr_emu_noise.so")  # libm sin/cos with 1-ulp noise (experiments)
+
+
+def _path(libm):
+    return LIB_PATH_NOISE if libm == "noise" else (LIB_PATH_LIBM if libm else LIB_PATH)
+
+
 def build(libm=False):
-    path = LIB_PATH_LIBM if libm else LIB_PATH
+    path = _path(libm)
     os.makedirs(os.path.dirname(path), exist_ok=True)
+    defs = ["-DILQR_TRIG_LIBM", "-DILQR_TRIG_NOISE"] if libm == "noise" else (["-DILQR_TRIG_LIBM"] if libm else [])
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
-                           "-Wno-unknown-pragmas", "-I" + os.path.join(ROOT, "include")] +
-                          (["-DILQR_TRIG_LIBM"] if libm else []) + ["-o", path, SRC])
+                           "-Wno-unknown-pragmas", "-Wno-maybe-uninitialized", "-I" + os.path.join(ROOT, "include")] +
+                          defs + ["-o", path, SRC])
 
 
 def lib(libm=False):
     if libm not in _libs:
-        path = LIB_PATH_LIBM if libm else LIB_PATH
+        path = _path(libm)
         if (not os.path.exists(path)) or any(os.path.getmtime(d) > os.path.getmtime(path) for d in DEPS):
             build(libm)
         L = C.CDLL(path)

@@ -130,9 +130,59 @@ def make_solver_fixture():
         s = R.RefSolver(R.DOUBLE_INTEGRATOR, 0.05, goal=[1.0, 1.0, 0.0, 0.0])
         cases["integrator_rand_T60_b%d" % b] = dict(trace_instance(s, xd[b], ud[b]), x0=xd[b], u0=ud[b], dt=0.05,
                                                     goal=[1.0, 1.0, 0.0, 0.0])
+    # warm start / MPC: iLQR::generate_trajectory(x_0) after a finished solve, src/ilqr_core.cpp:65-76.
+    # lambda / dlambda carry over from the first solve (TU statics, include/ilqr.h:17-18).  The *_native values come
+    # from the reference's own generate_trajectory(x_0); the checkpoints from the probe's replica of its loop, which
+    # tests/test_oracle_ref.py checks against the native call bit for bit.
+    rng = np.random.default_rng(77)
+    for b, (T, shift) in enumerate(((120, 0.01), (200, 0.05))):
+        xw, uw = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (T, 1))
+        x1 = xw + shift
+        s = R.RefSolver(R.ACROBOT, 0.02)
+        s.init(xw, uw)
+        s.iterate(1000)
+        d = dict(x0=xw, u0=uw, dt=0.02, x0_warm=x1, first_cost=s.cost, first_lambda=s.scalar("lam"),
+                 first_dlambda=s.scalar("dlam"), first_trips=s.count("loop_trips"))
+        d["warm_cost"] = s.warm_start(x1)
+        d["warm_xs"] = s.get("xs")
+        d["warm_us"] = s.get("us")
+        done = 0
+        for n in (1, 3, 10):
+            s.iterate(n - done)
+            done = n
+            for f in ("K", "k", "xs", "us"):
+                d["warm_it%d_%s" % (n, f)] = s.get(f)
+            d["warm_it%d_cost" % n] = s.cost
+            d["warm_it%d_lambda" % n] = s.scalar("lam")
+        s.iterate(1000)
+        d["warm_final_cost"], d["warm_final_trips"], d["warm_final_status"] = s.cost, s.count("loop_trips"), s.count("status")
+        nat = R.RefSolver(R.ACROBOT, 0.02)
+        nat.solve_native(xw, uw)
+        nat.warm_native(x1)
+        d["warm_final_cost_native"] = nat.cost
+        d["warm_final_xs_native"] = nat.get("xs")
+        # "continue": generate_trajectory() called once more on the finished warm solve (:78-102)
+        nat.resume_native()
+        d["resume_final_cost_native"] = nat.cost
+        s.resume()
+        s.iterate(1000)
+        d["resume_final_cost"], d["resume_trips"] = s.cost, s.count("loop_trips")
+        cases["acrobot_warm_b%d" % b] = d
     # keep the file small: the big per-checkpoint arrays only for a subset
     np.savez_compressed(os.path.join(HERE, "solver_golden.npz"), **pack(cases))
     return cases
+
+
+def make_csv_fixture():
+    """the result files the reference's own CLI writes (src/run_ilqr.cpp, output_to_csv src/ilqr_core.cpp:414-431)"""
+    import shutil
+    import subprocess
+    import tempfile
+    exe = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "run_iLQR")
+    for which in ("acrobot", "integrator"):
+        with tempfile.TemporaryDirectory() as d:
+            subprocess.run([exe, which], cwd=d, check=True, stdout=subprocess.DEVNULL)
+            shutil.copy(os.path.join(d, "ilqr_result.csv"), os.path.join(HERE, "ref_cli_%s.csv" % which))
 
 
 def make_leaf_fixture():
@@ -177,9 +227,15 @@ def make_leaf_fixture():
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     make_leaf_fixture()
+    make_csv_fixture()
     cases = make_solver_fixture()
     for name, d in cases.items():
-        print("%-28s init %.6f final %.12g trips %d status %s" % (
-            name, d["init_cost"], d["final_cost"], d["final_trips"], R.STATUS[d["final_status"]]))
+        if "init_cost" in d:
+            print("%-28s init %.6f final %.12g trips %d status %s" % (
+                name, d["init_cost"], d["final_cost"], d["final_trips"], R.STATUS[d["final_status"]]))
+        else:
+            print("%-28s first %.12g warm %.12g -> %.12g (native %.12g) resume %.12g (native %.12g)" % (
+                name, d["first_cost"], d["warm_cost"], d["warm_final_cost"], d["warm_final_cost_native"],
+                d["resume_final_cost"], d["resume_final_cost_native"]))
     for f in ("solver_golden.npz", "leaf_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

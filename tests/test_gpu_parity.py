@@ -366,6 +366,61 @@ def test_warm_start_matches_oracle():
         close(s.get("K")[b:b + 1], o.get("K")[None])
 
 
+@pytest.mark.parametrize("case", ["acrobot_warm_b0", "acrobot_warm_b1"])
+def test_warm_start_and_resume_against_reference_golden(golden_solver, case):
+    """ilqr_warm_start = iLQR::generate_trajectory(x_0) (src/ilqr_core.cpp:65-76), ilqr_resume = a repeated
+    generate_trajectory() (:78-102), lambda / dlambda carried over: against vectors written by the unmodified reference
+    (replica checkpoints, and the terminal costs of the reference's OWN warm-start / continue calls)"""
+    g = golden_solver
+    x0, u0 = g[case + "/x0"], g[case + "/u0"]
+    s = BatchILQR(abi.MODEL_ACROBOT, T=u0.shape[0], B=2, dt=float(g[case + "/dt"]))   # the same instance twice
+    s.generate_trajectory(np.stack([x0, x0]), np.stack([u0, u0]))
+    close(s.get("cost"), [g[case + "/first_cost"]] * 2)
+    close(s.get("lambda"), [g[case + "/first_lambda"]] * 2, 1e-9, 1e-300)
+    s.warm_start(np.stack([g[case + "/x0_warm"]] * 2))
+    close(s.get("cost"), [g[case + "/warm_cost"]] * 2)
+    close(s.get("xs"), np.stack([g[case + "/warm_xs"]] * 2))
+    close(s.get("us"), np.stack([g[case + "/warm_us"]] * 2))
+    done = 0
+    for n in (1, 3, 10):
+        s.iterate(n - done)
+        done = n
+        close(s.get("cost"), [g["%s/warm_it%d_cost" % (case, n)]] * 2)
+        close(s.get("lambda"), [g["%s/warm_it%d_lambda" % (case, n)]] * 2, 1e-9, 1e-300)
+        for f, name in (("K", "K"), ("k", "k"), ("xs", "xs"), ("us", "us")):
+            close(s.get(f), np.stack([g["%s/warm_it%d_%s" % (case, n, name)]] * 2), 1e-5)
+    s.solve()
+    close(s.get("cost"), [g[case + "/warm_final_cost_native"]] * 2)
+    s.generate_trajectory()                                                    # resume + solve
+    close(s.get("cost"), [g[case + "/resume_final_cost_native"]] * 2)
+    assert (s.get("status") != abi.RUNNING).all()
+
+
+def test_resume_reenters_the_loop():
+    """a solve that ran out of iterations continues for up to max_iter more after ilqr_resume (the reference's repeated
+    generate_trajectory(), src/ilqr_core.cpp:78-102); without it a finished handle stays finished.  GPU == oracle."""
+    p = abi.default_params()
+    p.max_iter = 6
+    B, T = 5, 80
+    x0, u0 = make_inputs(5, B, T, 4, 1, canonical_first=False)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, params=p)
+    s.generate_trajectory(x0, u0)
+    assert (s.get("status") == abi.EXIT_MAXITER).all() and (s.get("iters") == 6).all()
+    c6 = s.get("cost").copy()
+    s.solve()                                                                  # nothing is running: a no-op
+    assert np.array_equal(s.get("cost"), c6) and (s.get("iters") == 6).all()
+    s.generate_trajectory()
+    assert (s.get("iters") > 6).all() and (s.get("cost") < c6).all()
+    for b in range(B):
+        o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, params=p)
+        o.init(x0[b], u0[b])
+        o.iterate(100)
+        o.resume()
+        o.iterate(100)
+        close(s.get("cost")[b:b + 1], [o.cost])
+        assert s.get("iters")[b] == o.count("loop_trips")
+
+
 def test_iterate_granularity_and_determinism():
     """iterate(1) x N == iterate(N) bit for bit; a trajectory's result does not depend on the batch around it."""
     B, T = 64, 200
@@ -450,10 +505,6 @@ def test_f32_config3_sanity():
 HOST_BUILD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ilqr_b200", "host", "_build")
 
 
-def _read_csv(path):
-    rows = open(path).read().strip().split("\n")[1:]
-    return [np.array([float(v) for v in r.strip().rstrip(",").split(",")]) for r in rows]
-
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(HOST_BUILD, "run_iLQR")), reason="host binaries not built")
 @pytest.mark.parametrize("which,case", [("acrobot", "acrobot_cli_T499"), ("integrator", "integrator_cli_T99")])
@@ -463,12 +514,21 @@ def test_reference_cli_runs_on_the_gpu_path(tmp_path, golden_solver, which, case
                          timeout=300)
     assert out.returncode == 0, out.stderr
     assert "Run iLQR!" in out.stdout and "iLQR took:" in out.stdout          # src/run_ilqr.cpp:57,62
-    rows = _read_csv(tmp_path / "ilqr_result.csv")                            # src/ilqr_core.cpp:300,414-431
+    # the result file (src/ilqr_core.cpp:300,414-431) has the reference's exact format — same header bytes, same row
+    # structure, the terminal row ending in ", " with no newline — and is read by plot_results.py's own logic
+    from ilqr_b200 import export
     g = golden_solver
-    xs = g[case + "/final_xs"]
-    assert len(rows) == xs.shape[0]
-    assert np.allclose(rows[-1][:4], xs[-1], atol=2e-6)                       # %f keeps 6 decimals
-    assert np.allclose(np.stack([r[:4] for r in rows]), xs, atol=5e-5)
+    xs, us = g[case + "/final_xs"], g[case + "/final_us"]
+    ours = open(tmp_path / "ilqr_result.csv", "rb").read()
+    ref = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cli_%s.csv" % which), "rb").read()
+    assert ours.split(b"\n")[0] == ref.split(b"\n")[0]
+    assert ours.count(b"\n") == ref.count(b"\n") and ours.endswith(b", ") and not ours.endswith(b"\n")
+    assert [l.count(b",") for l in ours.split(b"\n")] == [l.count(b",") for l in ref.split(b"\n")]
+    states, controls = export.read_csv(tmp_path / "ilqr_result.csv", xs.shape[1], us.shape[1])
+    assert states.shape == xs.shape and controls.shape == us.shape           # T + 1 states, T controls
+    assert np.allclose(states[-1], xs[-1], atol=2e-6)                         # %f keeps 6 decimals
+    assert np.allclose(states, xs, atol=5e-5) and np.allclose(controls, us, atol=5e-4)
+    assert "Saved iLQR result to ilqr_result.csv" in out.stdout               # :430
     cost = float(out.stdout.split("cost ")[-1].split()[0])
     assert abs(cost - g[case + "/final_cost"]) <= 1e-6 * abs(cost)
 
@@ -487,6 +547,31 @@ def test_host_batch_entry_point(tmp_path, golden_solver):
     assert ok >= 4                                                            # FD-cost mode, bifurcations tolerated
     single = lines[6]
     assert abs(float(single[3]) - float(lines[0][3])) <= 1e-9 * abs(float(lines[0][3]))  # single API == batch entry 0
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(HOST_BUILD, "batch_demo")), reason="host binaries not built")
+def test_host_batch_export(tmp_path):
+    """iLQR::export_batch (whole batch, binary) and iLQR::output_to_csv(file, b) (one trajectory, the reference's CSV)"""
+    from ilqr_b200 import export
+    out = subprocess.run([os.path.join(HOST_BUILD, "batch_demo"), "24", "120", str(tmp_path / "res")], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    d = export.read_batch(tmp_path / "res.bin")
+    assert d["xs"].shape == (24, 121, 4) and d["us"].shape == (24, 120, 1)
+    lines = [l.split() for l in out.stdout.strip().split("\n")]
+    for b in range(6):
+        assert abs(float(lines[b][3]) - d["cost"][b]) <= 1e-9 * abs(d["cost"][b]) and int(lines[b][5]) == d["iters"][b]
+    assert (d["status"] != abi.RUNNING).all()
+    states, controls = export.read_csv(tmp_path / "res_b3.csv", 4, 1)
+    assert np.abs(states - d["xs"][3]).max() <= 5.1e-7 and np.abs(controls - d["us"][3]).max() <= 5.1e-7
+    # the same two files through the Python host layer
+    x0, u0 = make_inputs(12345, 24, 120, 4, 1)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=120, B=24, dt=0.02)
+    s.generate_trajectory(x0, u0)
+    s.export_batch(tmp_path / "py.bin")
+    s.output_to_csv(tmp_path / "py_b3.csv", 3)
+    assert open(tmp_path / "py.bin", "rb").read() == open(tmp_path / "res.bin", "rb").read()
+    assert open(tmp_path / "py_b3.csv", "rb").read() == open(tmp_path / "res_b3.csv", "rb").read()
 
 
 # ---------------------------------------------------------------------------------------------

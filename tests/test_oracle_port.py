@@ -180,6 +180,35 @@ def test_solve_against_reference_golden(golden_solver, case, model, kw):
     assert rel_err(o.get("xs"), g[case + "/final_xs"]) < 1e-5
 
 
+@pytest.mark.parametrize("case", ["acrobot_warm_b0", "acrobot_warm_b1"])
+def test_warm_start_and_resume_against_reference_golden(golden_solver, case):
+    """iLQR::generate_trajectory(x_0) (src/ilqr_core.cpp:65-76) and a second generate_trajectory() (:78-102) after a
+    finished solve, lambda / dlambda carried over (include/ilqr.h:17-18): the oracle against vectors written by the
+    unmodified reference — replica checkpoints plus the terminal cost of the reference's OWN warm-start call."""
+    g = golden_solver
+    o = O.OracleSolver(abi.MODEL_ACROBOT, float(g[case + "/dt"]))
+    o.init(g[case + "/x0"], g[case + "/u0"])
+    o.iterate(1000)
+    assert abs(o.cost - g[case + "/first_cost"]) <= REL * abs(o.cost)
+    assert abs(o.scalar("lam") - g[case + "/first_lambda"]) <= 1e-9 * abs(g[case + "/first_lambda"]) + 1e-300
+    c = o.warm_start(g[case + "/x0_warm"])
+    assert abs(c - g[case + "/warm_cost"]) <= REL * abs(c)
+    assert rel_err(o.get("xs"), g[case + "/warm_xs"]) < 1e-6 and rel_err(o.get("us"), g[case + "/warm_us"]) < 1e-6
+    done = 0
+    for n in (1, 3, 10):
+        o.iterate(n - done)
+        done = n
+        assert abs(o.cost - g["%s/warm_it%d_cost" % (case, n)]) <= REL * abs(o.cost), n
+        assert abs(o.scalar("lam") - g["%s/warm_it%d_lambda" % (case, n)]) <= 1e-9 * abs(o.scalar("lam")) + 1e-300, n
+        for f in ("K", "k", "xs", "us"):
+            assert rel_err(o.get(f), g["%s/warm_it%d_%s" % (case, n, f)]) < 1e-5, (n, f)
+    o.iterate(1000)
+    assert abs(o.cost - g[case + "/warm_final_cost_native"]) <= REL * abs(o.cost)
+    o.resume()
+    o.iterate(1000)
+    assert abs(o.cost - g[case + "/resume_final_cost_native"]) <= REL * abs(o.cost)
+
+
 def test_golden_headline_numbers(golden_solver):
     """The numbers SURVEY.md §8c quotes from the reference (canonical acrobot, T = 200 and the CLI's T = 499)."""
     g = golden_solver

@@ -57,3 +57,44 @@ def test_oracle_tracks_reference_on_fresh_instances(model, kw, T, dt):
         assert abs(r.cost - o.cost) <= 1e-7 * abs(r.cost)
         assert r.count("alpha_index") == o.count("alpha_index")
         assert np.abs(r.get("K") - o.get("K")).max() <= 1e-6 * np.abs(r.get("K")).max()
+
+
+def test_replica_warm_start_and_resume_equal_native():
+    """generate_trajectory(x_0) (src/ilqr_core.cpp:65-76) and a repeated generate_trajectory() (:78-102): the probe's
+    replica entry points land exactly where the reference's own calls land, lambda / dlambda carried over."""
+    rng = np.random.default_rng(8)
+    x0, u0 = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (110, 1))
+    x1 = x0 + 0.02
+    a, b = R.RefSolver(R.ACROBOT, 0.02), R.RefSolver(R.ACROBOT, 0.02)
+    a.solve_native(x0, u0)
+    a.warm_native(x1)
+    b.init(x0, u0)
+    b.iterate(1000)
+    b.warm_start(x1)
+    b.iterate(1000)
+    for f in ("xs", "us", "K", "k"):
+        assert np.array_equal(a.get(f), b.get(f)), f
+    assert a.cost == b.cost and a.scalar("lam") == b.scalar("lam") and a.scalar("dlam") == b.scalar("dlam")
+    a.resume_native()
+    b.resume()
+    b.iterate(1000)
+    for f in ("xs", "us", "K", "k"):
+        assert np.array_equal(a.get(f), b.get(f)), f
+    assert a.cost == b.cost
+
+
+def test_oracle_warm_start_tracks_reference():
+    rng = np.random.default_rng(9)
+    for trial in range(3):
+        x0, u0 = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (90, 1))
+        x1 = x0 + rng.uniform(-0.03, 0.03, 4)
+        r, o = R.RefSolver(R.ACROBOT, 0.02), O.OracleSolver(abi.MODEL_ACROBOT, 0.02)
+        r.init(x0, u0), o.init(x0, u0)
+        r.iterate(7), o.iterate(7)
+        cr, co = r.warm_start(x1), o.warm_start(x1)
+        assert abs(cr - co) <= 1e-9 * abs(cr)
+        assert np.abs(r.get("xs") - o.get("xs")).max() <= 1e-9 * np.abs(r.get("xs")).max()
+        r.iterate(4), o.iterate(4)
+        assert abs(r.cost - o.cost) <= 1e-7 * abs(r.cost)
+        assert r.scalar("lam") == o.scalar("lam")
+        assert np.abs(r.get("K") - o.get("K")).max() <= 1e-6 * np.abs(r.get("K")).max()
