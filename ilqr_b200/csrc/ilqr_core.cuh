@@ -277,6 +277,65 @@ ILQR_HD S ld_fresh(const S *p) {
 #endif
 }
 
+/* ---- finite differences ----------------------------------------------------------------------------------------
+ * The reference's stencils (include/finite_diff.h:22-86, src/derivatives.cpp:15-144) with eps = 1e-3, evaluated in
+ * DOUBLE whatever the scalar type S of the solve: in f32 a central difference of the Euler step carries
+ * ulp(x) / (2 eps) ~ 3e-5 of relative noise, which the Riccati recursion over hundreds of unstable steps amplifies
+ * until the f32 solve has nothing to do with the f64 one after a handful of trips (measured, tests: K off by O(1)
+ * after 5 trips), and a cost Hessian stencil is pure noise (ulp(4000) / 4 eps^2 ~ 60).  Forming the differences in
+ * double and rounding the RESULT to S keeps the derivative arrays accurate to S's own precision; everything else
+ * of an f32 solve (rollouts, backward pass, boxQP, storage) stays f32.  For S = double nothing changes. */
+template <int D, typename W>
+ILQR_HD void fd_perturb(const W *v, int a, W da, int b, W db, W *out) { /* v[q] (+ da if q == a) (+ db if q == b) */
+#pragma unroll
+  for (int q = 0; q < D; q++) {
+    W t = v[q];
+    if (q == a) t += da;
+    if (q == b) t += db;
+    out[q] = t;
+  }
+}
+template <class Model, typename S>
+struct FiniteDiff {
+  typedef double W;
+  static constexpr int N = Model::N, M = Model::M, NM = N + M;
+  struct Point {
+    W x[N], u[M], mp[16], dt, eps;
+  };
+  ILQR_HD static void load(const SolveParams<S> &P, const S *x, const S *u, Point &p) {
+#pragma unroll
+    for (int i = 0; i < N; i++) p.x[i] = W(x[i]);
+#pragma unroll
+    for (int i = 0; i < M; i++) p.u[i] = W(u[i]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) p.mp[i] = W(P.mp[i]);
+    p.dt = W(P.dt);
+    p.eps = W(P.fd_eps);
+  }
+  /* column j < n of [fx | fu] by two full Euler steps (finite_diff_jacobian, finite_diff.h:35-47) */
+  ILQR_HD static void column_full(const Point &p, int j, S *col) {
+    W xa[N], fp[N], fm[N];
+    fd_perturb<N, W>(p.x, j, p.eps, -1, W(0), xa);
+    integrate<Model, W>(xa, p.u, p.mp, p.dt, fp);
+    fd_perturb<N, W>(p.x, j, -p.eps, -1, W(0), xa);
+    integrate<Model, W>(xa, p.u, p.mp, p.dt, fm);
+#pragma unroll
+    for (int r = 0; r < N; r++) col[r] = S((fp[r] - fm[r]) / (2 * p.eps));
+  }
+  /* column j (not a configuration variable) with the configuration-dependent part of the dynamics already formed */
+  ILQR_HD static void column_shared(const Point &p, const typename Model::template Config<W> &cf, int j, S *col) {
+    W xa[N], ua[M], fp[N], fm[N];
+    fd_perturb<N, W>(p.x, j, p.eps, -1, W(0), xa);
+    fd_perturb<M, W>(p.u, j - N, p.eps, -1, W(0), ua);
+    integrate_cfg<Model, W>(cf, xa, ua, p.mp, p.dt, fp);
+    fd_perturb<N, W>(p.x, j, -p.eps, -1, W(0), xa);
+    fd_perturb<M, W>(p.u, j - N, -p.eps, -1, W(0), ua);
+    integrate_cfg<Model, W>(cf, xa, ua, p.mp, p.dt, fm);
+#pragma unroll
+    for (int r = 0; r < N; r++) col[r] = S((fp[r] - fm[r]) / (2 * p.eps));
+  }
+};
+
 template <class Model, typename S, int CD, class Exec>
 struct Core {
   static constexpr int N = Model::N, M = Model::M, NM = N + M;
@@ -341,27 +400,30 @@ struct Core {
 
   ILQR_HD void cost_stencil(int o, bool terminal, const S *x, const S *u, S *cf) { cost_stencil_s(P, o, terminal, x, u, cf); }
   /* the same without an instance (the phase kernels of ilqr_phases.cuh run one stencil output per thread) */
-  ILQR_HD static void cost_stencil_s(const SolveParams<S> &P, int o, bool terminal, const S *x, const S *u, S *cf) {
-    const S eps = P.fd_eps;
-    const S *mp = P.mp;
-    S xa[N], ua[M];
-    auto fx = [&](const S *xv, const S *uv) -> S { return terminal ? Model::final_cost(xv, mp) : Model::cost(xv, uv, mp); };
+  ILQR_HD static void cost_stencil_s(const SolveParams<S> &P, int o, bool terminal, const S *x_, const S *u_, S *cf) {
+    typedef typename FiniteDiff<Model, S>::W W; /* evaluated in double, the result rounded to S (see FiniteDiff) */
+    typename FiniteDiff<Model, S>::Point pt;
+    FiniteDiff<Model, S>::load(P, x_, u_, pt);
+    const W eps = pt.eps;
+    const W *mp = pt.mp, *x = pt.x, *u = pt.u;
+    W xa[N], ua[M];
+    auto fx = [&](const W *xv, const W *uv) -> W { return terminal ? Model::final_cost(xv, mp) : Model::cost(xv, uv, mp); };
     if (o < N) { /* finite_diff_gradient wrt x, finite_diff.h:22-33 */
-      perturb<N>(x, o, eps, -1, S(0), xa);
-      const S p = fx(xa, u);
-      perturb<N>(x, o, -eps, -1, S(0), xa);
-      const S m = fx(xa, u);
-      cf[o] = (p - m) / (2 * eps);
+      fd_perturb<N, W>(x, o, eps, -1, W(0), xa);
+      const W p = fx(xa, u);
+      fd_perturb<N, W>(x, o, -eps, -1, W(0), xa);
+      const W m = fx(xa, u);
+      cf[o] = S((p - m) / (2 * eps));
       return;
     }
     o -= N;
     if (!terminal) {
       if (o < M) {
-        perturb<M>(u, o, eps, -1, S(0), ua);
-        const S p = Model::cost(x, ua, mp);
-        perturb<M>(u, o, -eps, -1, S(0), ua);
-        const S m = Model::cost(x, ua, mp);
-        cf[N + o] = (p - m) / (2 * eps);
+        fd_perturb<M, W>(u, o, eps, -1, W(0), ua);
+        const W p = Model::cost(x, ua, mp);
+        fd_perturb<M, W>(u, o, -eps, -1, W(0), ua);
+        const W m = Model::cost(x, ua, mp);
+        cf[N + o] = S((p - m) / (2 * eps));
         return;
       }
       o -= M;
@@ -369,15 +431,15 @@ struct Core {
     if (o < kNxx) { /* finite_diff_hessian wrt x, finite_diff.h:67-86 */
       int i, j;
       tri_index(o, N, i, j);
-      perturb<N>(x, i, eps, j, eps, xa);
-      const S pp = fx(xa, u);
-      perturb<N>(x, i, -eps, j, eps, xa);
-      const S mpv = fx(xa, u);
-      perturb<N>(x, i, eps, j, -eps, xa);
-      const S pm = fx(xa, u);
-      perturb<N>(x, i, -eps, j, -eps, xa);
-      const S mm = fx(xa, u);
-      const S v = (pp - mpv - pm + mm) / (4 * eps * eps);
+      fd_perturb<N, W>(x, i, eps, j, eps, xa);
+      const W pp = fx(xa, u);
+      fd_perturb<N, W>(x, i, -eps, j, eps, xa);
+      const W mpv = fx(xa, u);
+      fd_perturb<N, W>(x, i, eps, j, -eps, xa);
+      const W pm = fx(xa, u);
+      fd_perturb<N, W>(x, i, -eps, j, -eps, xa);
+      const W mm = fx(xa, u);
+      const S v = S((pp - mpv - pm + mm) / (4 * eps * eps));
       cf[ix_cxx(i, j)] = v;
       cf[ix_cxx(j, i)] = v;
       return;
@@ -387,15 +449,15 @@ struct Core {
     if (o < kNuu) {
       int i, j;
       tri_index(o, M, i, j);
-      perturb<M>(u, i, eps, j, eps, ua);
-      const S pp = Model::cost(x, ua, mp);
-      perturb<M>(u, i, -eps, j, eps, ua);
-      const S mpv = Model::cost(x, ua, mp);
-      perturb<M>(u, i, eps, j, -eps, ua);
-      const S pm = Model::cost(x, ua, mp);
-      perturb<M>(u, i, -eps, j, -eps, ua);
-      const S mm = Model::cost(x, ua, mp);
-      const S v = (pp - mpv - pm + mm) / (4 * eps * eps);
+      fd_perturb<M, W>(u, i, eps, j, eps, ua);
+      const W pp = Model::cost(x, ua, mp);
+      fd_perturb<M, W>(u, i, -eps, j, eps, ua);
+      const W mpv = Model::cost(x, ua, mp);
+      fd_perturb<M, W>(u, i, eps, j, -eps, ua);
+      const W pm = Model::cost(x, ua, mp);
+      fd_perturb<M, W>(u, i, -eps, j, -eps, ua);
+      const W mm = Model::cost(x, ua, mp);
+      const S v = S((pp - mpv - pm + mm) / (4 * eps * eps));
       cf[ix_cuu(i, j)] = v;
       cf[ix_cuu(j, i)] = v;
       return;
@@ -403,14 +465,13 @@ struct Core {
     o -= kNuu;
     if (o < N * M) { /* calculate_cxu, src/derivatives.cpp:114-144 (its own stencil) */
       const int i = o / M, j = o % M;
-      S xp[N], xm[N], up[M], um[M];
-      perturb<N>(x, i, eps, -1, S(0), xp);
-      perturb<N>(x, i, -eps, -1, S(0), xm);
-      perturb<M>(u, j, eps, -1, S(0), up);
-      perturb<M>(u, j, -eps, -1, S(0), um);
-      const S v =
-          (Model::cost(xp, up, mp) - Model::cost(xm, up, mp) - Model::cost(xp, um, mp) + Model::cost(xm, um, mp)) /
-          (4 * (eps * eps));
+      W xp[N], xm[N], up[M], um[M];
+      fd_perturb<N, W>(x, i, eps, -1, W(0), xp);
+      fd_perturb<N, W>(x, i, -eps, -1, W(0), xm);
+      fd_perturb<M, W>(u, j, eps, -1, W(0), up);
+      fd_perturb<M, W>(u, j, -eps, -1, W(0), um);
+      const S v = S((Model::cost(xp, up, mp) - Model::cost(xm, up, mp) - Model::cost(xp, um, mp) + Model::cost(xm, um, mp)) /
+                    (4 * (eps * eps)));
       cf[ix_cxu(i, j)] = v;
       cf[ix_cux(j, i)] = v;
     }
@@ -456,17 +517,16 @@ struct Core {
           const int task = base + lane;
           if (task >= n_a) return;
           const int t = task / kNumConfigVars, j = nth_config_var(task - t * kNumConfigVars);
-          S x[N], u[M], xa[N], fp[N], fm[N];
+          S x[N], u[M], col[N];
 #pragma unroll
           for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
 #pragma unroll
           for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
-          perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
-          integrate<Model, S>(xa, u, P.mp, P.dt, fp);
-          perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
-          integrate<Model, S>(xa, u, P.mp, P.dt, fm);
+          typename FiniteDiff<Model, S>::Point pt;
+          FiniteDiff<Model, S>::load(P, x, u, pt);
+          FiniteDiff<Model, S>::column_full(pt, j, col);
 #pragma unroll
-          for (int r = 0; r < N; r++) sl.F[((size_t)t * NM + j) * N + r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+          for (int r = 0; r < N; r++) sl.F[((size_t)t * NM + j) * N + r] = col[r];
         });
       }
     }
@@ -474,24 +534,21 @@ struct Core {
       ex.lanes([&](int lane, Lane &) {
         const int t = base + lane;
         if (t >= T) return;
-        S x[N], u[M], xa[N], ua[M], fp[N], fm[N];
+        S x[N], u[M], col[N];
 #pragma unroll
         for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
 #pragma unroll
         for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
-        typename Model::template Config<S> cf;
-        Model::configure(x, P.mp, cf);
+        typename FiniteDiff<Model, S>::Point pt;
+        FiniteDiff<Model, S>::load(P, x, u, pt);
+        typename Model::template Config<typename FiniteDiff<Model, S>::W> cf;
+        Model::configure(pt.x, pt.mp, cf);
 #pragma unroll
         for (int j = 0; j < NM; j++) {
           if (is_config_var(j)) continue;
-          perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
-          perturb<M>(u, j - N, P.fd_eps, -1, S(0), ua);
-          integrate_cfg<Model, S>(cf, xa, ua, P.mp, P.dt, fp);
-          perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
-          perturb<M>(u, j - N, -P.fd_eps, -1, S(0), ua);
-          integrate_cfg<Model, S>(cf, xa, ua, P.mp, P.dt, fm);
+          FiniteDiff<Model, S>::column_shared(pt, cf, j, col);
 #pragma unroll
-          for (int r = 0; r < N; r++) sl.F[((size_t)t * NM + j) * N + r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+          for (int r = 0; r < N; r++) sl.F[((size_t)t * NM + j) * N + r] = col[r];
         }
       });
     }

@@ -79,14 +79,17 @@ int launch_cd(ilqr_handle *h, int op, int n_iters, double scalar) {
   if (!(std::is_same<Model, Acrobot>::value && std::is_same<S, double>::value && h->desc.cost_deriv == ILQR_COST_ANALYTIC))
     return ilqr_fail(h, ILQR_E_INVALID, "experiment build: acrobot f64 analytic only");
   if constexpr (std::is_same<Model, Acrobot>::value && std::is_same<S, double>::value) {
-    const bool pack16 = h->lanes == 16 || (h->lanes == 0 && h->desc.B >= 32768);
+    const bool pack16 = h->lanes == 16;
     return pack16 ? launch_t<Model, S, kCostAnalytic, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostAnalytic, 32>(h, op, n_iters, scalar);
   } else {
     return ILQR_E_INVALID;
   }
 #else
-  /* two trajectories per warp once the batch can fill the schedulers that way (4 warps per scheduler on 148 SMs) */
-  const bool pack = h->lanes == 16 || (h->lanes == 0 && h->desc.B >= 32768);
+  /* Two trajectories per warp (16 lanes each) only when asked for (ILQR_B200_LANES=16: experiments and the tests of
+   * that decomposition).  Round 1 chose it for batches that fill the machine; those now run on the batch-lockstep
+   * phase kernels (ilqr_phases.cuh), which do the same job — issue the narrow phases once for several trajectories —
+   * for every phase, so the default paths are the 32-lane kernel and the phase kernels. */
+  const bool pack = h->lanes == 16;
   if (h->desc.cost_deriv == ILQR_COST_ANALYTIC)
     return pack ? launch_t<Model, S, kCostAnalytic, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostAnalytic, 32>(h, op, n_iters, scalar);
   return pack ? launch_t<Model, S, kCostFD, 16>(h, op, n_iters, scalar) : launch_t<Model, S, kCostFD, 32>(h, op, n_iters, scalar);

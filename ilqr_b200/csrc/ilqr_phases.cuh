@@ -161,36 +161,24 @@ struct Phases {
    * part == kNumConfigVars: every other column, the configuration-dependent part of the dynamics formed once
    * (Core::derivative_sweep, passes A and B). */
   ILQR_HD static void sweep_task(const SolveParams<S> &P, const S *xs, const S *us, S *F, int part, int t) {
-    S x[N], u[M], xa[N], fp[N], fm[N];
+    S x[N], u[M], col[N];
     load_run<N>(x, xs + (size_t)t * N);
     load_run<M>(u, us + (size_t)t * M);
+    typedef FiniteDiff<Model, S> FD; /* differences formed in double, rounded to S (ilqr_core.cuh) */
+    typename FD::Point pt;
+    FD::load(P, x, u, pt);
     if (part < CoreT::kNumConfigVars) {
       const int j = CoreT::nth_config_var(part);
-      CoreT::template perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
-      integrate<Model, S>(xa, u, P.mp, P.dt, fp);
-      CoreT::template perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
-      integrate<Model, S>(xa, u, P.mp, P.dt, fm);
-      S col[N];
-#pragma unroll
-      for (int r = 0; r < N; r++) col[r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+      FD::column_full(pt, j, col);
       store_run<N>(F + ((size_t)t * NM + j) * N, col);
       return;
     }
-    S ua[M];
-    typename Model::template Config<S> cf;
-    Model::configure(x, P.mp, cf);
+    typename Model::template Config<typename FD::W> cf;
+    Model::configure(pt.x, pt.mp, cf);
 #pragma unroll
     for (int j = 0; j < NM; j++) {
       if (CoreT::is_config_var(j)) continue;
-      CoreT::template perturb<N>(x, j, P.fd_eps, -1, S(0), xa);
-      CoreT::template perturb<M>(u, j - N, P.fd_eps, -1, S(0), ua);
-      integrate_cfg<Model, S>(cf, xa, ua, P.mp, P.dt, fp);
-      CoreT::template perturb<N>(x, j, -P.fd_eps, -1, S(0), xa);
-      CoreT::template perturb<M>(u, j - N, -P.fd_eps, -1, S(0), ua);
-      integrate_cfg<Model, S>(cf, xa, ua, P.mp, P.dt, fm);
-      S col[N];
-#pragma unroll
-      for (int r = 0; r < N; r++) col[r] = (fp[r] - fm[r]) / (2 * P.fd_eps);
+      FD::column_shared(pt, cf, j, col);
       store_run<N>(F + ((size_t)t * NM + j) * N, col);
     }
   }

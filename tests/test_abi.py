@@ -17,7 +17,7 @@ HEADER = os.path.join(ROOT, "include", "ilqr_b200.h")
 def declared_functions():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(ilqr_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(ilqr_[a-z0-9_]+)\s*\(", text)))
 
 
 @pytest.fixture(scope="module")

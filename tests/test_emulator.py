@@ -100,6 +100,42 @@ def test_phase_engine_source_equals_oracle_bit_for_bit(golden_solver, case, mode
     lockstep(model, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), True, lanes=1, cost_deriv=cd, **kw)
 
 
+def test_sixteen_lane_decomposition_batch_of_64():
+    """the two-per-warp decomposition on a batch: 64 acrobot instances in the reference's FD mode and 64 double-integrator
+    instances (m = 2) against the oracle bit for bit over their first trips, and in float against the 32-lane
+    decomposition of the same source"""
+    import bench
+    x0, u0 = bench.synth_inputs_cpu(64, 120, 4321)
+    for b in range(64):
+        o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02)
+        e = E.EmuSolver(abi.MODEL_ACROBOT, 0.02, libm=True, lanes=16)
+        assert o.init(x0[b], u0[b]) == e.init(x0[b], u0[b])
+        o.iterate(6), e.iterate(6)
+        for f in ARR:
+            assert np.array_equal(o.get(f), e.get(f)), (b, f)
+        assert o.cost == e.cost and o.scalar("lam") == e.scalar("lam") and o.count("alpha_index") == e.count("alpha_index")
+    rng = np.random.default_rng(6)
+    for b in range(64):
+        xd, ud = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (40, 2))
+        kw = dict(goal=[1.0, 1.0, 0.0, 0.0], cost_deriv=abi.COST_FD if b % 2 else abi.COST_ANALYTIC)
+        o = O.OracleSolver(abi.MODEL_DOUBLE_INTEGRATOR, 0.05, **kw)
+        e = E.EmuSolver(abi.MODEL_DOUBLE_INTEGRATOR, 0.05, libm=True, lanes=16, **kw)
+        assert o.init(xd, ud) == e.init(xd, ud)
+        o.iterate(50), e.iterate(50)
+        for f in ARR:
+            assert np.array_equal(o.get(f), e.get(f)), (b, f)
+        assert o.count("status") == e.count("status") and o.count("loop_trips") == e.count("loop_trips")
+    for b in range(16):
+        a = E.EmuSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC, dtype=abi.F32, lanes=16)
+        c = E.EmuSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC, dtype=abi.F32, lanes=32)
+        d = E.EmuSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC, dtype=abi.F32, lanes=1)
+        for s_ in (a, c, d):
+            s_.init(x0[b], u0[b])
+            s_.iterate(8)
+        for f in ARR:
+            assert np.array_equal(a.get(f), c.get(f)) and np.array_equal(a.get(f), d.get(f)), (b, f)
+
+
 def test_warm_start_kernel_source_equals_oracle():
     rng = np.random.default_rng(3)
     x0, u0 = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (90, 1))

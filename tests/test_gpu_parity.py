@@ -110,14 +110,16 @@ def test_acrobot_single_phases(cost_deriv):
 @pytest.mark.parametrize("cost_deriv", [abi.COST_FD, abi.COST_ANALYTIC])
 def test_acrobot_checkpoints(cost_deriv):
     """K, k, xs, us, cost after N = 1, 5, 20 loop trips (SURVEY.md §7 parity methodology (ii))."""
-    B, T = 48, 200
+    B, T = 96, 200
     x0, u0 = make_inputs(12345, B, T, 4, 1)
     s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cost_deriv)
     s.set_initial(x0, u0)
     done = 0
     # the reference's own FD cost Hessian carries ~5e-10 of rounding noise (SURVEY.md §7 "FD noise budget"),
     # which a 1-ulp change in x_T re-rolls: the FD-cost mode reaches the 1e-6 line a little earlier
-    fracs = ((1, 1.0), (5, 0.9), (20, 0.8)) if cost_deriv == abi.COST_FD else ((1, 1.0), (5, 1.0), (20, 0.85))
+    # gates = measured rates minus a margin (profiles/r2_attribution.md: K at 20 trips agrees for 97.5 % of 2048 instances in
+    # closed-form mode and 96.5 % in FD mode, and the same fractions appear when the ORACLE's sin/cos is perturbed by 1 ulp)
+    fracs = ((1, 1.0), (5, 0.95), (20, 0.9)) if cost_deriv == abi.COST_FD else ((1, 1.0), (5, 1.0), (20, 0.93))
     for n, frac in fracs:
         s.iterate(n - done)
         done = n
@@ -130,21 +132,31 @@ def test_acrobot_checkpoints(cost_deriv):
 
 
 def test_acrobot_termination():
-    """Terminal cost at termination (parity methodology (iii)).  The last trips of a solve accept or
-    reject on the SIGN of a cost change that is pure rounding noise (src/ilqr_core.cpp:206), so the
-    trip count may legitimately differ by a few between two correct implementations; the terminal
-    cost may not."""
-    B, T = 64, 200
+    """Terminal cost at termination (parity methodology (iii)) on 512 instances, gated at the measured rate minus a
+    margin: 98.1 % of 2048 instances end within 1e-6 of the oracle and 99.6 % within 1e-3, and perturbing the ORACLE's
+    own sin/cos by one ulp gives the same two numbers (profiles/r2_attribution.md).  The last trips of a solve accept
+    or reject on the SIGN of a cost change that is pure rounding noise (src/ilqr_core.cpp:206), so the trip count may
+    legitimately differ by a few between two correct implementations; the terminal cost may not."""
+    B, T = 512, 200
     x0, u0 = make_inputs(12345, B, T, 4, 1)
-    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
     s.generate_trajectory(x0, u0)
-    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 101, snap)
+    r = O.solve_range(abi.make_desc(model=abi.MODEL_ACROBOT, T=T, dt=0.02, cost_deriv=abi.COST_ANALYTIC), x0, u0, 0, B)
     g = gpu_snap(s)
     assert (g["status"] != abi.RUNNING).all()
-    close(g["cost"], ref["cost"], frac=0.9)
-    close(g["cost"], ref["cost"], rtol=1e-3, frac=0.95)
-    assert np.mean(g["trips"] == ref["trips"]) >= 0.7
-    close(g["xs"], ref["xs"], rtol=1e-5, frac=0.85)
+    close(g["cost"], r["cost"], frac=0.97)
+    close(g["cost"], r["cost"], rtol=1e-3, frac=0.99)
+    assert np.mean(g["trips"] == r["iters"]) >= 0.9
+    # the reference's own derivative mode (finite-difference costs), a smaller sample with the full state compared
+    B = 96
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02)
+    s.generate_trajectory(x0[:B], u0[:B])
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0[:B], u0[:B], 0.02, 101, snap)
+    g = gpu_snap(s)
+    close(g["cost"], ref["cost"], frac=0.94)
+    close(g["cost"], ref["cost"], rtol=1e-3, frac=0.97)
+    assert np.mean(g["trips"] == ref["trips"]) >= 0.85
+    close(g["xs"], ref["xs"], rtol=1e-5, frac=0.92)
 
 
 def test_acrobot_golden_reference(golden_solver):
@@ -160,12 +172,15 @@ def test_acrobot_golden_reference(golden_solver):
         close(s.get(f), np.stack([g[c + "/" + name] for c in cases]), 1e-7, 1e-9)
     s.set_initial(x0, u0)
     done = 0
-    for n, frac in ((1, 1.0), (5, 0.8), (20, 0.66)):
+    # all six at 1 and 5 trips.  After 5 trips instance b3 (an ill-conditioned one: it ends on lambda > lambdaMax at cost 860)
+    # sits at 1.2e-6 in K and 5e-6 in k, the other five below 1e-7: the gate there is 1e-5 on every instance and 1e-6 on five of six.
+    # At 20 trips b2 is on a line-search branch point (tests/test_oracle_port.py finds the same for the oracle).
+    for n, rtol, frac in ((1, 1e-6, 1.0), (5, 1e-5, 1.0), (5, 1e-6, 0.83), (20, 1e-6, 0.66)):
         s.iterate(n - done)
         done = n
         for f in ("K", "k", "xs", "us"):
-            close(s.get(f), np.stack([g["%s/it%d_%s" % (c, n, f)] for c in cases]), frac=frac)
-        close(s.get("cost"), [g["%s/it%d_cost" % (c, n)] for c in cases], frac=frac)
+            close(s.get(f), np.stack([g["%s/it%d_%s" % (c, n, f)] for c in cases]), rtol=rtol, frac=frac)
+        close(s.get("cost"), [g["%s/it%d_cost" % (c, n)] for c in cases], rtol=rtol, frac=frac)
     s.solve()
     close(s.get("cost"), [g[c + "/final_cost"] for c in cases], frac=0.66)
 
@@ -257,6 +272,35 @@ def test_phase_engine_equals_warp_engine_bit_for_bit(model, cd, dtype, T, B, kw,
     assert (ph.get("status") != abi.RUNNING).all()
     # the phase engine really ran its own kernels: four launches per trip, not one per iterate call
     assert ph.launch_count > wp.launch_count + 8
+
+
+@pytest.mark.parametrize("model,cd,dtype,T,kw", [
+    (abi.MODEL_ACROBOT, abi.COST_FD, abi.F64, 200, {}),
+    (abi.MODEL_ACROBOT, abi.COST_FD, abi.F64, 120, dict(u_min=[-1.5], u_max=[1.5])),
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F32, 500, {}),
+    (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, abi.F64, 60, dict(goal=[1.0, 1.0, 0.0, 0.0])),
+    (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_ANALYTIC, abi.F32, 60, dict(goal=[1.0, 1.0, 0.0, 0.0])),
+])
+def test_sixteen_lane_kernel_batch(model, cd, dtype, T, kw, monkeypatch):
+    """the two-trajectories-per-warp instantiation of the warp kernel (ILQR_B200_LANES=16), batch of 96: FD mode, the
+    double integrator (m = 2) and float, against the default engine bit for bit at every checkpoint"""
+    B = 96
+    n, m = abi.MODEL_DIMS[model]
+    x0, u0 = make_inputs(515, B, T, n, m)
+    dt = 0.02 if model == abi.MODEL_ACROBOT else 0.05
+    ref = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, **kw)
+    monkeypatch.setenv("ILQR_B200_LANES", "16")
+    s16 = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, **kw)
+    monkeypatch.delenv("ILQR_B200_LANES")
+    ref.set_initial(x0, u0)
+    s16.set_initial(x0, u0)
+    done = 0
+    for n_it in (1, 5, 101):
+        ref.iterate(n_it - done)
+        s16.iterate(n_it - done)
+        done = n_it
+        for f in ALL_FIELDS:
+            assert np.array_equal(ref.get(f), s16.get(f)), (n_it, f)
 
 
 def test_phase_engine_iterate_resume_and_warm_start():
@@ -470,32 +514,87 @@ def test_full_size_config2_properties():
     # rolling the returned controls out open-loop reproduces the returned states and cost (consistency of xs/us/cost)
     xs, us = s.get("xs"), s.get("us")
     idx = np.random.default_rng(0).choice(B, 24, replace=False)
+    idx2 = np.arange(0, B, 8)  # 512 instances against the oracle's own solves
     for b in idx:
         o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, cost_deriv=abi.COST_ANALYTIC)
         c = o.init(xs[b, 0], us[b])
         close([c], cost[b:b + 1], 1e-9, 1e-9)
         close(o.get("xs")[None], xs[b:b + 1], 1e-8, 1e-8)
     # a sample of instances against the oracle's own solves
-    ref = oracle_batch(abi.MODEL_ACROBOT, x0[idx], u0[idx], 0.02, 101, snap, cost_deriv=abi.COST_ANALYTIC)
-    close(cost[idx], ref["cost"], frac=0.85)
+    r = O.solve_range(abi.make_desc(model=abi.MODEL_ACROBOT, T=T, dt=0.02, cost_deriv=abi.COST_ANALYTIC),
+                      np.ascontiguousarray(x0[idx2]), np.ascontiguousarray(u0[idx2]), 0, len(idx2))
+    close(cost[idx2], r["cost"], frac=0.97)
+    close(cost[idx2], r["cost"], rtol=1e-3, frac=0.99)
     # re-running is bit-reproducible
     s2 = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
     s2.generate_trajectory(x0, u0)
     assert (s2.get("cost") == cost).all() and (s2.get("iters") == trips).all()
 
 
-def test_f32_config3_sanity():
-    """BASELINE config 3 arithmetic (f32, FD fx/fu, analytic cost derivatives) at a small batch: one backward
-    pass against the f64 oracle at f32-level tolerance, and the solve must reduce the cost."""
-    B, T = 32, 500
+def _f32_inputs(B, T):
+    """instances whose f32 rounding is exact in f64, so the oracle and the f32 kernels start from the same numbers"""
     x0, u0 = make_inputs(12345, B, T, 4, 1)
+    return x0.astype(np.float32).astype(np.float64), u0.astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("T,budget1,budget5", [(200, dict(K=2e-4, k=3e-3, cost=1e-3), dict(med_K=2e-3, frac=0.8)),
+                                               (500, dict(K=2e-4, k=5e-3, cost=2e-3), dict(med_K=2e-2, frac=0.6))])
+@pytest.mark.parametrize("head", ["rows", "thread"])
+def test_f32_parity_vs_f64_oracle(T, budget1, budget5, head, monkeypatch):
+    """BASELINE configs[2] arithmetic (f32, FD fx/fu, closed-form cost derivatives) against the f64 ORACLE on every
+    instance, at a stated f32 budget.  The finite differences are formed in double and rounded to f32 (ilqr_core.cuh,
+    FiniteDiff): with f32 differences the Jacobians carry 3e-5 of noise and K is off by 2e-3 (median) after ONE trip and
+    by O(1) after five; with this scheme (measured on the CPU build of the same source, 24 instances) the first trip
+    agrees to K 2e-5, k 5e-4, cost 2e-4 in the worst instance.  Later trips drift apart at f32 rounding amplified by the
+    unstable recursion and a growing fraction of instances takes another line-search branch, exactly as f64-vs-f64 does
+    at 1-ulp level (profiles/r2_attribution.md) but from a 1e-7 instead of a 1e-16 seed: after five trips the median
+    instance still agrees to 5e-5 (T = 200) / 1e-3 (T = 500)."""
+    monkeypatch.setenv("ILQR_B200_ROWS_MAX", "0" if head == "thread" else "1000000")
+    B = 64
+    x0, u0 = _f32_inputs(B, T)
     s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, dtype=abi.F32, cost_deriv=abi.COST_ANALYTIC)
     c0 = s.init_traj(x0, u0)
-    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 0, snap, cost_deriv=abi.COST_ANALYTIC)
-    close(c0, ref["cost"], 2e-4, 1e-3)
-    s.iterate(10)
+    ref0 = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 0, snap, cost_deriv=abi.COST_ANALYTIC)
+    close(c0, ref0["cost"], 2e-5, 1e-3)
+    s.iterate(1)
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 1, snap, cost_deriv=abi.COST_ANALYTIC)
+    g = gpu_snap(s)
+    assert (g["alpha_index"] == ref["alpha_index"]).mean() >= 0.95
+    same = g["alpha_index"] == ref["alpha_index"]          # an instance on another line-search branch is not comparable
+    close(g["K"][same], ref["K"][same], budget1["K"], 1e-6)
+    close(g["k"][same], ref["k"][same], budget1["k"], 1e-6)
+    close(g["cost"][same], ref["cost"][same], budget1["cost"], 0)
+    s.iterate(4)
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 5, snap, cost_deriv=abi.COST_ANALYTIC)
+    g = gpu_snap(s)
+    eK = inst_err(g["K"], ref["K"], 1e-6)
+    assert np.median(eK) <= budget5["med_K"], np.median(eK)
+    assert (eK <= 5e-2).mean() >= budget5["frac"], (eK <= 5e-2).mean()
+    assert (inst_err(g["cost"], ref["cost"], 0) <= 1e-2).mean() >= budget5["frac"]
+
+
+def test_f32_config3_termination_statistics():
+    """Where f32 solves end, next to the f64 oracle on the same instances.  At T = 500 the reference's own 100-iteration
+    cap is what stops most solves IN F64 TOO (21 of 24 in the CPU measurement): the MAXITER share of configs[2] is a
+    property of the problem, not of the arithmetic.  At T = 200 the f32 solves end within 1e-2 of the f64 cost for most
+    instances and never above the initial cost."""
+    B, T = 48, 200
+    x0, u0 = _f32_inputs(B, T)
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, dtype=abi.F32, cost_deriv=abi.COST_ANALYTIC)
+    c0 = s.init_traj(x0, u0)
+    s.solve()
+    ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 101, snap, cost_deriv=abi.COST_ANALYTIC)
     c1 = s.get("cost")
-    assert np.isfinite(c1).all() and (c1 <= c0).all() and c1.mean() < 0.8 * c0.mean()
+    assert np.isfinite(c1).all() and (c1 <= c0).all() and (s.get("status") != abi.RUNNING).all()
+    assert (inst_err(c1, ref["cost"], 0) <= 1e-2).mean() >= 0.6
+    assert abs(s.get("iters").mean() - ref["trips"].mean()) <= 12
+    # T = 500: the iteration cap stops the f64 oracle as well
+    B5, T5 = 12, 500
+    x5, u5 = _f32_inputs(B5, T5)
+    s5 = BatchILQR(abi.MODEL_ACROBOT, T=T5, B=B5, dt=0.02, dtype=abi.F32, cost_deriv=abi.COST_ANALYTIC)
+    s5.generate_trajectory(x5, u5)
+    ref5 = oracle_batch(abi.MODEL_ACROBOT, x5, u5, 0.02, 101, snap, cost_deriv=abi.COST_ANALYTIC)
+    assert (ref5["status"] == abi.EXIT_MAXITER).mean() >= 0.6 and (s5.get("status") == abi.EXIT_MAXITER).mean() >= 0.6
 
 
 # ---------------------------------------------------------------------------------------------

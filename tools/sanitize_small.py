@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """A small workload for compute-sanitizer (memcheck / racecheck / synccheck): both models, both cost-derivative modes,
-both lane decompositions, a few loop trips each.
+every engine path a default build can take — the batch-lockstep phase kernels with each of their three trip heads
+(8 lanes per trajectory, one thread per trajectory, one warp per trajectory) and the persistent 32-lane warp kernel —
+a few loop trips each.  `--lanes16` adds the optional two-per-warp instantiation (ILQR_B200_LANES=16).
 
     compute-sanitizer --tool racecheck python tools/sanitize_small.py
 """
@@ -12,8 +14,18 @@ sys.path.insert(0, ROOT)
 from ilqr_b200 import abi  # noqa: E402
 from ilqr_b200.solver import BatchILQR, make_inputs  # noqa: E402
 
-for lanes in ("32", "16"):
-    os.environ["ILQR_B200_LANES"] = lanes
+PATHS = [("phase/rows", dict(ILQR_B200_ROWS_MAX="1000000", ILQR_B200_WARP_PRE_MAX="0", ILQR_B200_HANDOVER="0")),
+         ("phase/thread", dict(ILQR_B200_ROWS_MAX="0", ILQR_B200_WARP_PRE_MAX="0", ILQR_B200_HANDOVER="0")),
+         ("phase/warp-head", dict(ILQR_B200_ROWS_MAX="0", ILQR_B200_WARP_PRE_MAX="1000000", ILQR_B200_HANDOVER="0")),
+         ("phase+handover", dict(ILQR_B200_HANDOVER="5", ILQR_B200_CHECK_EVERY="1")),
+         ("warp32", dict(ILQR_B200_ENGINE="warp"))]
+if "--lanes16" in sys.argv:
+    PATHS.append(("warp16", dict(ILQR_B200_LANES="16")))
+KEYS = sorted({k for _, e in PATHS for k in e})
+for name, env in PATHS:
+    for k in KEYS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
     for model, T, m in ((abi.MODEL_ACROBOT, 37, 1), (abi.MODEL_DOUBLE_INTEGRATOR, 19, 2)):
         for cd in (abi.COST_ANALYTIC, abi.COST_FD):
             B = 9
@@ -24,7 +36,9 @@ for lanes in ("32", "16"):
             s.iterate(3)
             s.warm_start(x0 + 0.01)
             s.iterate(2)
+            s.resume()
+            s.iterate(4)
             c = s.get("cost")
-            print("lanes", lanes, "model", model, "cost_deriv", cd, "cost[0] %.6g" % c[0], flush=True)
+            print("path", name, "model", model, "cost_deriv", cd, "cost[0] %.6g" % c[0], flush=True)
             s.close()
 print("done")
