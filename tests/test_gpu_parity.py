@@ -254,6 +254,8 @@ def test_phase_engine_equals_warp_engine_bit_for_bit(model, cd, dtype, T, B, kw,
     # (ilqr_phase_launch.cuh); each is forced here in turn: 8 lanes per trajectory / 1 thread / 32 lanes
     monkeypatch.setenv("ILQR_B200_ROWS_MAX", "0" if head == "thread" else "1000000")
     monkeypatch.setenv("ILQR_B200_WARP_PRE_MAX", "1000000" if head == "warp" else "0")
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")  # lockstep rounds to the end (by default a batch this small goes straight
+    #                                                to the persistent kernel, ilqr_phase_launch.cuh: kPhaseHandover)
     n, m = abi.MODEL_DIMS[model]
     x0, u0 = make_inputs(2024, B, T, n, m)
     dt = 0.02 if model == abi.MODEL_ACROBOT else 0.05
@@ -303,8 +305,32 @@ def test_sixteen_lane_kernel_batch(model, cd, dtype, T, kw, monkeypatch):
             assert np.array_equal(ref.get(f), s16.get(f)), (n_it, f)
 
 
-def test_phase_engine_iterate_resume_and_warm_start():
+@pytest.mark.parametrize("handover,check", [(150, 1), (250, 3), (40, 8)])
+def test_phase_engine_hands_the_tail_to_the_persistent_kernel(handover, check, monkeypatch):
+    """lockstep rounds while many trajectories run, then the persistent warp kernel for the survivors' remaining trips
+    (the default for large batches): same bits as either engine alone, wherever the switch happens"""
+    B, T = 300, 200
+    x0, u0 = make_inputs(77, B, T, 4, 1)
+    monkeypatch.setenv("ILQR_B200_HANDOVER", str(handover))
+    monkeypatch.setenv("ILQR_B200_CHECK_EVERY", str(check))
+    a = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+    b = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC, flags=abi.FLAG_ENGINE_WARP)
+    a.generate_trajectory(x0, u0)
+    b.generate_trajectory(x0, u0)
+    for f in ALL_FIELDS:
+        assert np.array_equal(a.get(f), b.get(f)), f
+    assert a.launch_count > b.launch_count + 8        # it did run lockstep rounds first
+    a.set_initial(x0, u0)
+    b.set_initial(x0, u0)
+    a.iterate(30)
+    b.iterate(30)
+    for f in ALL_FIELDS:
+        assert np.array_equal(a.get(f), b.get(f)), f
+
+
+def test_phase_engine_iterate_resume_and_warm_start(monkeypatch):
     """iterate in uneven chunks (active list rebuilt by each call), then warm start and continue: equal to one call"""
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")
     B, T = 96, 120
     x0, u0 = make_inputs(31, B, T, 4, 1)
     a = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
@@ -454,7 +480,7 @@ def test_resume_reenters_the_loop():
     s.solve()                                                                  # nothing is running: a no-op
     assert np.array_equal(s.get("cost"), c6) and (s.get("iters") == 6).all()
     s.generate_trajectory()
-    assert (s.get("iters") > 6).all() and (s.get("cost") < c6).all()
+    assert (s.get("iters") > 6).all() and (s.get("cost") <= c6).all() and (s.get("cost") < c6).any()
     for b in range(B):
         o = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, params=p)
         o.init(x0[b], u0[b])
@@ -537,8 +563,8 @@ def _f32_inputs(B, T):
     return x0.astype(np.float32).astype(np.float64), u0.astype(np.float32).astype(np.float64)
 
 
-@pytest.mark.parametrize("T,budget1,budget5", [(200, dict(K=2e-4, k=3e-3, cost=1e-3), dict(med_K=2e-3, frac=0.8)),
-                                               (500, dict(K=2e-4, k=5e-3, cost=2e-3), dict(med_K=2e-2, frac=0.6))])
+@pytest.mark.parametrize("T,budget1,budget5", [(200, dict(K=1e-4, k=2e-3, cost=1e-3, same=0.95), dict(med_K=5e-4, frac=0.85)),
+                                               (500, dict(K=1e-3, k=2e-2, cost=3e-2, same=0.9), dict(med_K=5e-3, frac=0.5))])
 @pytest.mark.parametrize("head", ["rows", "thread"])
 def test_f32_parity_vs_f64_oracle(T, budget1, budget5, head, monkeypatch):
     """BASELINE configs[2] arithmetic (f32, FD fx/fu, closed-form cost derivatives) against the f64 ORACLE on every
@@ -547,19 +573,23 @@ def test_f32_parity_vs_f64_oracle(T, budget1, budget5, head, monkeypatch):
     by O(1) after five; with this scheme (measured on the CPU build of the same source, 24 instances) the first trip
     agrees to K 2e-5, k 5e-4, cost 2e-4 in the worst instance.  Later trips drift apart at f32 rounding amplified by the
     unstable recursion and a growing fraction of instances takes another line-search branch, exactly as f64-vs-f64 does
-    at 1-ulp level (profiles/r2_attribution.md) but from a 1e-7 instead of a 1e-16 seed: after five trips the median
-    instance still agrees to 5e-5 (T = 200) / 1e-3 (T = 500)."""
+    at 1-ulp level (profiles/r2_attribution.md) but from a 1e-7 instead of a 1e-16 seed.  Gates = the GPU measurement
+    on these 64 instances (profiles/r2_f32_parity.txt, tools/exp_f32_parity.py) with a margin: after one trip every
+    same-branch instance within K 2.3e-5 / k 3.5e-4 / cost 1.9e-4 (T = 200) and 2.3e-4 / 5.6e-3 / 9.4e-3 (T = 500); after
+    five trips the median K within 3.6e-5 / 5.1e-4 and 95 % / 67 % of the instances within 5e-2."""
     monkeypatch.setenv("ILQR_B200_ROWS_MAX", "0" if head == "thread" else "1000000")
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")
     B = 64
     x0, u0 = _f32_inputs(B, T)
     s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, dtype=abi.F32, cost_deriv=abi.COST_ANALYTIC)
     c0 = s.init_traj(x0, u0)
     ref0 = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 0, snap, cost_deriv=abi.COST_ANALYTIC)
-    close(c0, ref0["cost"], 2e-5, 1e-3)
+    close(c0, ref0["cost"], 2e-4, 1e-3, frac=0.95)   # a 200- to 500-step rollout in f32
+    close(c0, ref0["cost"], 2e-3, 1e-3)
     s.iterate(1)
     ref = oracle_batch(abi.MODEL_ACROBOT, x0, u0, 0.02, 1, snap, cost_deriv=abi.COST_ANALYTIC)
     g = gpu_snap(s)
-    assert (g["alpha_index"] == ref["alpha_index"]).mean() >= 0.95
+    assert (g["alpha_index"] == ref["alpha_index"]).mean() >= budget1["same"]
     same = g["alpha_index"] == ref["alpha_index"]          # an instance on another line-search branch is not comparable
     close(g["K"][same], ref["K"][same], budget1["K"], 1e-6)
     close(g["k"][same], ref["k"][same], budget1["k"], 1e-6)
