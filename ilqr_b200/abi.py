@@ -16,6 +16,8 @@ MODEL_USER_BASE = 100  # ids of models registered at run time (register_model)
 F64, F32 = 0, 1
 COST_FD, COST_ANALYTIC = 0, 1
 FLAG_ENGINE_WARP = 1  # ilqr_desc.flags
+FLAG_CLAMP_ROLLOUT, FLAG_ANALYTIC_DYN = 2, 4
+FLAG_FAST_FMA = 8
 RUNNING, EXIT_GRAD, EXIT_TOLFUN, EXIT_LAMBDA_MAX, EXIT_MAXITER = 0, 1, 2, 3, 4
 STATUS_NAMES = {0: "RUNNING", 1: "GRAD", 2: "TOLFUN", 3: "LAMBDA_MAX", 4: "MAXITER"}
 

@@ -127,6 +127,9 @@ namespace {
 int launch(ilqr_handle *h, int op, int n_iters, double scalar) {
   if (h->desc.model_id >= ILQR_MODEL_USER_BASE)
     return h->desc.dtype == ILQR_F32 ? launch_user<float>(h, op, n_iters, scalar) : launch_user<double>(h, op, n_iters, scalar);
+  if (h->desc.flags & ILQR_FLAG_FAST_FMA)
+    return h->desc.model_id == ILQR_MODEL_ACROBOT ? ilqr_launch_acrobot_fma(h, op, n_iters, scalar)
+                                                  : ilqr_launch_double_integrator_fma(h, op, n_iters, scalar);
   if (h->desc.model_id == ILQR_MODEL_ACROBOT) return ilqr_launch_acrobot(h, op, n_iters, scalar);
   return ilqr_launch_double_integrator(h, op, n_iters, scalar);
 }
@@ -236,6 +239,10 @@ int ilqr_create(const ilqr_desc *desc, ilqr_handle **out) {
   if (desc->B < 1 || desc->T < 1) return fail(nullptr, ILQR_E_INVALID, "B and T must be positive");
   if (!(desc->dt > 0)) return fail(nullptr, ILQR_E_INVALID, "dt must be positive");
   if ((desc->flags & ~ILQR_FLAG_ALL) != 0 || desc->reserved1 != 0) return fail(nullptr, ILQR_E_INVALID, "unknown flags");
+  if ((desc->flags & ILQR_FLAG_ANALYTIC_DYN) && desc->model_id >= ILQR_MODEL_USER_BASE)
+    return fail(nullptr, ILQR_E_INVALID, "ILQR_FLAG_ANALYTIC_DYN: built-in models only");
+  if ((desc->flags & ILQR_FLAG_FAST_FMA) && desc->model_id >= ILQR_MODEL_USER_BASE)
+    return fail(nullptr, ILQR_E_INVALID, "ILQR_FLAG_FAST_FMA: built-in models only (user models are compiled without contraction)");
   {
     SolveParams<double> chk;
     if (make_solve_params<double>(*desc, &chk) != 0) return fail(nullptr, ILQR_E_INVALID, "bad solver parameters");
@@ -309,9 +316,13 @@ int ilqr_iterate(ilqr_handle *h, int n_iters) {
   if (!h->initialised) return fail(h, ILQR_E_STATE, "ilqr_iterate before ilqr_set_initial");
   if (n_iters < 0) return fail(h, ILQR_E_INVALID, "n_iters must be >= 0");
   DeviceGuard g(h->desc.device);
-  if (!h->engine_warp && h->desc.model_id < ILQR_MODEL_USER_BASE) /* the batch-lockstep phase kernels (ilqr_phases.cuh) */
+  if (!h->engine_warp && h->desc.model_id < ILQR_MODEL_USER_BASE) { /* the batch-lockstep phase kernels (ilqr_phases.cuh) */
+    if (h->desc.flags & ILQR_FLAG_FAST_FMA)
+      return h->desc.model_id == ILQR_MODEL_ACROBOT ? ilqr_phase_iterate_acrobot_fma(h, n_iters)
+                                                    : ilqr_phase_iterate_double_integrator_fma(h, n_iters);
     return h->desc.model_id == ILQR_MODEL_ACROBOT ? ilqr_phase_iterate_acrobot(h, n_iters)
                                                   : ilqr_phase_iterate_double_integrator(h, n_iters);
+  }
   return launch(h, kOpIterate, n_iters, 0.0);
 }
 

@@ -57,6 +57,7 @@ constexpr int kMaxAlpha = 16;  /* ILQR_MAX_ALPHA */
 enum { kRunning = 0, kExitGrad = 1, kExitTolFun = 2, kExitLambdaMax = 3, kExitMaxIter = 4 };
 enum { kCostFD = 0, kCostAnalytic = 1 };
 enum { kRollOpen = 0, kRollWarm = 1, kRollClosed = 2 };
+enum { kFlagClampRollout = 2, kFlagAnalyticDyn = 4 }; /* = ILQR_FLAG_CLAMP_ROLLOUT, ILQR_FLAG_ANALYTIC_DYN */
 
 /* every constant of the solve, in the scalar type the path computes in */
 template <typename S>
@@ -69,6 +70,7 @@ struct SolveParams {
   S u_min[4], u_max[4];
   S mp[16];
   QPParams<S> qp;
+  int flags;  /* ILQR_FLAG_* of include/ilqr_b200.h that change the arithmetic: kFlagClampRollout, kFlagAnalyticDyn */
   int bulk_f; /* host-set: every tile of the per-warp Jacobian buffer starts 16-byte aligned (bulk copy allowed) */
   int bulk_c; /* the same for the per-warp buffer of finite-difference cost derivatives */
 };
@@ -295,6 +297,16 @@ ILQR_HD void fd_perturb(const W *v, int a, W da, int b, W db, W *out) { /* v[q] 
     out[q] = t;
   }
 }
+/* does the model twin offer a closed-form Jacobian (Model::dynamics_jac)?  Optional: user models may leave it out */
+template <class M, class = void>
+struct HasDynamicsJac {
+  static constexpr bool value = false;
+};
+template <class M>
+struct HasDynamicsJac<M, decltype(M::template dynamics_jac<double>(nullptr, nullptr, nullptr, nullptr, nullptr), void())> {
+  static constexpr bool value = true;
+};
+
 template <class Model, typename S>
 struct FiniteDiff {
   typedef double W;
@@ -321,6 +333,23 @@ struct FiniteDiff {
     integrate<Model, W>(xa, p.u, p.mp, p.dt, fm);
 #pragma unroll
     for (int r = 0; r < N; r++) col[r] = S((fp[r] - fm[r]) / (2 * p.eps));
+  }
+  /* OPT-IN (kFlagAnalyticDyn): every column of [fx | fu] of the Euler step x + dt f(x, u) from the model's closed-form
+   * Jacobian; F[j * N + r] = d x'_r / d (x|u)_j.  Not the reference's arithmetic (it differs from the central
+   * differences by their O(eps^2) truncation term, ~3e-8), hence a flag. */
+  ILQR_HD static void jacobian_analytic(const Point &p, S *F) {
+    if constexpr (HasDynamicsJac<Model>::value) {
+      W A[N * N], Bm[N * M];
+      Model::template dynamics_jac<W>(p.x, p.u, p.mp, A, Bm);
+#pragma unroll
+      for (int j = 0; j < N; j++)
+#pragma unroll
+        for (int r = 0; r < N; r++) F[j * N + r] = S((r == j ? W(1) : W(0)) + A[r * N + j] * p.dt);
+#pragma unroll
+      for (int j = 0; j < M; j++)
+#pragma unroll
+        for (int r = 0; r < N; r++) F[(N + j) * N + r] = S(Bm[r * M + j] * p.dt);
+    }
   }
   /* column j (not a configuration variable) with the configuration-dependent part of the dynamics already formed */
   ILQR_HD static void column_shared(const Point &p, const typename Model::template Config<W> &cf, int j, S *col) {
@@ -510,6 +539,24 @@ struct Core {
 
   ILQR_HD void derivative_sweep() {
     const int T = P.T;
+    if ((P.flags & kFlagAnalyticDyn) && HasDynamicsJac<Model>::value) { /* opt-in: closed-form Jacobians, one lane per timestep */
+      for (int base = 0; base < T; base += G) {
+        ex.lanes([&](int lane, Lane &) {
+          const int t = base + lane;
+          if (t >= T) return;
+          S x[N], u[M], Fc[NM * N];
+#pragma unroll
+          for (int i = 0; i < N; i++) x[i] = tr.xs[t * N + i];
+#pragma unroll
+          for (int i = 0; i < M; i++) u[i] = tr.us[t * M + i];
+          typename FiniteDiff<Model, S>::Point pt;
+          FiniteDiff<Model, S>::load(P, x, u, pt);
+          FiniteDiff<Model, S>::jacobian_analytic(pt, Fc);
+#pragma unroll
+          for (int e = 0; e < NM * N; e++) sl.F[(size_t)t * NM * N + e] = Fc[e];
+        });
+      }
+    } else {
     if constexpr (kNumConfigVars > 0) {
       const int n_a = T * kNumConfigVars;
       for (int base = 0; base < n_a; base += G) {
@@ -551,6 +598,7 @@ struct Core {
           for (int r = 0; r < N; r++) sl.F[((size_t)t * NM + j) * N + r] = col[r];
         }
       });
+    }
     }
     if constexpr (CD == kCostFD) {
       const int n_c = T * kStencilStep;
@@ -880,6 +928,7 @@ struct Core {
         for (int i = 0; i < N; i++) a.add(Kt[j * N + i] * (x[i] - xhat[i]));
         v += a.v;
       }
+      if (P.flags & kFlagClampRollout) v = clampd(v, P.u_min[j], P.u_max[j]); /* opt-in: "the right way", :327-329 */
       uc[j] = v;
     }
     cost += Model::cost(x, uc, P.mp); /* :324 */

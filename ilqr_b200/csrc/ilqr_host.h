@@ -54,5 +54,10 @@ int ilqr_launch_double_integrator(ilqr_handle *h, int op, int n_iters, double sc
 /* up to n_iters loop trips for every running instance on the phase engine (ilqr_phase_launch.cuh) */
 int ilqr_phase_iterate_acrobot(ilqr_handle *h, int n_iters);
 int ilqr_phase_iterate_double_integrator(ilqr_handle *h, int n_iters);
+/* the same four from the translation units built with fused multiply-add contraction (ilqr_variant.h) */
+int ilqr_launch_acrobot_fma(ilqr_handle *h, int op, int n_iters, double scalar);
+int ilqr_launch_double_integrator_fma(ilqr_handle *h, int op, int n_iters, double scalar);
+int ilqr_phase_iterate_acrobot_fma(ilqr_handle *h, int n_iters);
+int ilqr_phase_iterate_double_integrator_fma(ilqr_handle *h, int n_iters);
 
 #endif

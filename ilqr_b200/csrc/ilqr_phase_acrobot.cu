@@ -1,5 +1,6 @@
 /* ilqr_phase_acrobot.cu — the batch-lockstep phase kernels (ilqr_phases.cuh) of the built-in Acrobot twin: f64 / f32,
  * finite-difference / closed-form cost derivatives. */
+#include "ilqr_variant.h"
 #include "ilqr_phase_launch.cuh"
 
-int ilqr_phase_iterate_acrobot(ilqr_handle *h, int n_iters) { return ilqr::phase_iterate<ilqr::Acrobot>(h, n_iters); }
+int ILQR_ENTRY(ilqr_phase_iterate_acrobot)(ilqr_handle *h, int n_iters) { return ilqr::phase_iterate<ilqr::Acrobot>(h, n_iters); }

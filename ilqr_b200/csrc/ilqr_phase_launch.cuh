@@ -8,6 +8,7 @@
 
 #include <stdlib.h>
 
+#include "ilqr_variant.h"
 #include "ilqr_host.h"
 #include "ilqr_phases.cuh"
 #include "params.h"
@@ -144,8 +145,8 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
   CU(h, cudaGetLastError());
   if (bound > 0 && trip < max_trips) { /* hand the survivors to the persistent kernel for their remaining trips */
     const int left = n_iters - trip;
-    return Model::M == 1 && Model::N == 4 && h->desc.model_id == ILQR_MODEL_ACROBOT ? ilqr_launch_acrobot(h, kOpIterate, left, 0.0)
-                                                                                     : ilqr_launch_double_integrator(h, kOpIterate, left, 0.0);
+    return h->desc.model_id == ILQR_MODEL_ACROBOT ? ILQR_ENTRY(ilqr_launch_acrobot)(h, kOpIterate, left, 0.0)
+                                                  : ILQR_ENTRY(ilqr_launch_double_integrator)(h, kOpIterate, left, 0.0);
   }
   return ILQR_OK;
 }

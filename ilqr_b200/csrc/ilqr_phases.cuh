@@ -167,6 +167,14 @@ struct Phases {
     typedef FiniteDiff<Model, S> FD; /* differences formed in double, rounded to S (ilqr_core.cuh) */
     typename FD::Point pt;
     FD::load(P, x, u, pt);
+    if ((P.flags & kFlagAnalyticDyn) && HasDynamicsJac<Model>::value) { /* opt-in: closed-form Jacobians, all columns at once */
+      if (part != 0) return;
+      S Fc[NM * N];
+      FD::jacobian_analytic(pt, Fc);
+#pragma unroll
+      for (int j = 0; j < NM; j++) store_run<N>(F + ((size_t)t * NM + j) * N, Fc + j * N);
+      return;
+    }
     if (part < CoreT::kNumConfigVars) {
       const int j = CoreT::nth_config_var(part);
       FD::column_full(pt, j, col);
@@ -545,6 +553,7 @@ struct Phases {
 #pragma unroll
         for (int i = 0; i < N; i++) acc.add(Kt[j * N + i] * (x[i] - xh[i]));
         v += acc.v;
+        if (P.flags & kFlagClampRollout) v = clampd(v, P.u_min[j], P.u_max[j]); /* opt-in: "the right way", :327-329 */
         uc[j] = v;
       }
       cost += Model::cost(x, uc, mp); /* :324 */
@@ -1141,9 +1150,15 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) phase_pre_warp_kern
   core.store_state();
 }
 
-constexpr int kRolloutThreads = 64;
+#ifndef ILQR_ROLLOUT_THREADS
+#define ILQR_ROLLOUT_THREADS 64
+#endif
+#ifndef ILQR_ROLLOUT_MINB
+#define ILQR_ROLLOUT_MINB 1
+#endif
+constexpr int kRolloutThreads = ILQR_ROLLOUT_THREADS;
 template <class Model, typename S, int CD>
-__global__ void __launch_bounds__(kRolloutThreads) phase_rollout_kernel(const __grid_constant__ PArgs<S> a) {
+__global__ void __launch_bounds__(kRolloutThreads, ILQR_ROLLOUT_MINB) phase_rollout_kernel(const __grid_constant__ PArgs<S> a) {
   using Ph = Phases<Model, S, CD>;
   constexpr int N = Model::N, M = Model::M;
   const int n_act = a.buf.n_act[a.parity];

@@ -98,6 +98,49 @@ struct Acrobot {
     configure(x, mp, cf);
     dynamics_cfg(cf, x, u, mp, dx);
   }
+  /* OPT-IN (ILQR_FLAG_ANALYTIC_DYN; not in the reference, which only has finite differences and lists analytic
+   * Jacobians as future work, notes.md:15,45): closed-form Jacobian of dynamics(), A[i * N + j] = d dx_i / d x_j,
+   * Bm[i * M + j] = d dx_i / d u_j.  With qdd = H^-1 r:  d qdd / d z = H^-1 (d r / d z - (d H / d z) qdd).  Same
+   * expressions in the same order as oracle/ilqr_oracle.c: acrobot_dynamics_jac. */
+  template <typename S>
+  ILQR_HD static void dynamics_jac(const S *x, const S *u, const S *mp, S *A, S *Bm) {
+    const S I1 = 1, I2 = 1, l1 = 1, l2 = 1, m1 = 1, m2 = 1, g = S(9.81);
+    const S lc1 = S(0.5) * l1, lc2 = S(0.5) * l2;
+    const S q0 = x[0], q1 = x[1], qd0 = x[2], qd1 = x[3];
+    S sn[3], cs[3];
+    sincos_det3(q1, q0, q0 + q1, sn, cs);
+    const S c2 = cs[0], s2 = sn[0], c1 = cs[1], c12 = cs[2];
+    const S a = m2 * l1 * lc2, b = m2 * l2 * lc2;
+    const S H00 = I1 + I2 + m2 * l1 * l1 + 2 * a * c2, H01 = I2 + a * c2, H11 = I2;
+    const S det = H00 * H11 - H01 * H01;
+    const S invdet = S(1) / det;
+    const S Hi00 = H11 * invdet, Hi01 = -H01 * invdet, Hi11 = H00 * invdet;
+    S dx[N];
+    dynamics(x, u, mp, dx);
+    const S qdd0 = dx[2], qdd1 = dx[3];
+    S dr0[4], dr1[4]; /* d r / d z - (d H / d z) qdd for z = q0, q1, qd0, qd1 */
+    dr0[0] = -(m1 * g * lc1 * c1 + m2 * g * (l1 * c1 + lc2 * c12));
+    dr1[0] = -(m2 * g * lc2 * c12);
+    dr0[1] = ((2 * a * qd0 * qd1 + b * qd1 * qd1) * c2 - m2 * g * lc2 * c12) + s2 * (2 * a * qdd0 + a * qdd1);
+    dr1[1] = (-(a * c2 * qd0 * qd0) - m2 * g * lc2 * c12) + s2 * (a * qdd0);
+    dr0[2] = 2 * a * s2 * qd1;
+    dr1[2] = -(2 * a * s2 * qd0);
+    dr0[3] = 2 * a * s2 * qd0 + 2 * b * s2 * qd1;
+    dr1[3] = S(0);
+#pragma unroll
+    for (int i = 0; i < 16; i++) A[i] = S(0);
+    A[0 * 4 + 2] = S(1);
+    A[1 * 4 + 3] = S(1);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      A[2 * 4 + j] = Hi00 * dr0[j] + Hi01 * dr1[j];
+      A[3 * 4 + j] = Hi01 * dr0[j] + Hi11 * dr1[j];
+    }
+    Bm[0] = S(0);
+    Bm[1] = S(0);
+    Bm[2] = Hi01;
+    Bm[3] = Hi11;
+  }
   /* Acrobot::cost :83-92 — Ks = Kd = 0, Kr = 0.1: the reference still evaluates 0 * (e0^2 + e1^2) + 0 * (e2^2 + e3^2) +
    * Kr^2 u^2.  While every |x_i| <= 1e150 the two sums of squares are finite and non-negative, so the state terms
    * are exactly +0 and (+0 + +0) + r == r bit for bit: the 14 operations behind them are skipped (3 % of the
@@ -151,6 +194,18 @@ struct DoubleIntegrator {
     dx[1] = x[3];
     dx[2] = u[0] / mass;
     dx[3] = u[1] / mass;
+  }
+  template <typename S>
+  ILQR_HD static void dynamics_jac(const S *, const S *, const S *, S *A, S *Bm) { /* opt-in, see Acrobot::dynamics_jac */
+    const S mass = 1;
+#pragma unroll
+    for (int i = 0; i < 16; i++) A[i] = S(0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) Bm[i] = S(0);
+    A[0 * 4 + 2] = S(1);
+    A[1 * 4 + 3] = S(1);
+    Bm[2 * 2 + 0] = S(1) / mass;
+    Bm[3 * 2 + 1] = S(1) / mass;
   }
   static constexpr unsigned kConfigVars = 0; /* nothing to share between perturbed points */
   template <typename S>

@@ -114,6 +114,7 @@ inline int make_solve_params(const ilqr_desc &d, SolveParams<S> *out) {
   P.qp.min_step = S(p.qp_min_step);
   P.qp.armijo = S(p.qp_armijo);
   P.qp.clamp_tol = S(p.qp_clamp_tol);
+  P.flags = d.flags & (kFlagClampRollout | kFlagAnalyticDyn);
   P.bulk_f = 0;
   return 0;
 }

@@ -52,7 +52,16 @@ extern "C" {
 /* ilqr_desc.flags */
 #define ILQR_FLAG_ENGINE_WARP 1    /* run ilqr_iterate / ilqr_solve on the persistent warp-per-trajectory kernel instead of
                                       the batch-lockstep phase kernels (identical results) */
-#define ILQR_FLAG_ALL (ILQR_FLAG_ENGINE_WARP)
+#define ILQR_FLAG_CLAMP_ROLLOUT 2  /* OPT-IN, changes results: the control a rollout applies is clamped to [u_min, u_max]
+                                      ("the right way" the reference comments out, src/ilqr_core.cpp:322-329; by
+                                      default rollouts are unclamped like the reference's) */
+#define ILQR_FLAG_ANALYTIC_DYN 4   /* OPT-IN, changes results: fx, fu from the model twin's closed-form Jacobian
+                                      (Model::dynamics_jac) instead of the reference's central differences
+                                      (src/derivatives.cpp:15-26; the reference lists this as future work, notes.md:15,45) */
+#define ILQR_FLAG_FAST_FMA 8       /* kernels built WITH fused multiply-add contraction: faster (dot products lose half their
+                                      dependent chain), results within 1e-6 of the default build after a handful of trips
+                                      but not bit-identical to the reference's no-FMA arithmetic.  Built-in models only. */
+#define ILQR_FLAG_ALL (ILQR_FLAG_ENGINE_WARP | ILQR_FLAG_CLAMP_ROLLOUT | ILQR_FLAG_ANALYTIC_DYN | ILQR_FLAG_FAST_FMA)
 
 /* error codes */
 #define ILQR_OK 0

@@ -134,6 +134,53 @@ static double di_cost(const double *goal, const double *x, const double *u) {
 }
 static double di_final_cost(const double *goal, const double *x) { return di_quad(goal, x, 10.0); }
 
+/* OPT-IN, not in the reference (ILQR_FLAG_ANALYTIC_DYN; the reference only has finite differences and lists analytic
+ * Jacobians as future work, notes.md:15,45): closed-form Jacobian of Acrobot::dynamics, A[i][j] = d dx_i / d x_j (4 x 4
+ * row-major), Bm[i] = d dx_i / d u.  With qdd = H^-1 r:  d qdd / d z = H^-1 (d r / d z - (d H / d z) qdd). */
+static void acrobot_dynamics_jac(const double *x, const double *u, double *A, double *Bm) {
+  const double I1 = 1, I2 = 1, l1 = 1, l2 = 1, m1 = 1, m2 = 1, g = 9.81;
+  const double lc1 = 0.5 * l1, lc2 = 0.5 * l2;
+  const double q0 = x[0], q1 = x[1], qd0 = x[2], qd1 = x[3];
+  const double c2 = cos(q1), s2 = sin(q1), c1 = cos(q0), c12 = cos(q0 + q1);
+  const double a = m2 * l1 * lc2, b = m2 * l2 * lc2;
+  const double H00 = I1 + I2 + m2 * l1 * l1 + 2 * a * c2, H01 = I2 + a * c2, H11 = I2;
+  const double det = H00 * H11 - H01 * H01;
+  const double invdet = 1.0 / det;
+  const double Hi00 = H11 * invdet, Hi01 = -H01 * invdet, Hi11 = H00 * invdet;
+  double dx[4];
+  acrobot_dynamics(x, u, dx);
+  const double qdd0 = dx[2], qdd1 = dx[3];
+  double dr0[4], dr1[4]; /* d r / d z - (d H / d z) qdd for z = q0, q1, qd0, qd1 */
+  dr0[0] = -(m1 * g * lc1 * c1 + m2 * g * (l1 * c1 + lc2 * c12));
+  dr1[0] = -(m2 * g * lc2 * c12);
+  dr0[1] = ((2 * a * qd0 * qd1 + b * qd1 * qd1) * c2 - m2 * g * lc2 * c12) + s2 * (2 * a * qdd0 + a * qdd1);
+  dr1[1] = (-(a * c2 * qd0 * qd0) - m2 * g * lc2 * c12) + s2 * (a * qdd0);
+  dr0[2] = 2 * a * s2 * qd1;
+  dr1[2] = -(2 * a * s2 * qd0);
+  dr0[3] = 2 * a * s2 * qd0 + 2 * b * s2 * qd1;
+  dr1[3] = 0.0;
+  for (int i = 0; i < 16; i++) A[i] = 0.0;
+  A[0 * 4 + 2] = 1.0;
+  A[1 * 4 + 3] = 1.0;
+  for (int j = 0; j < 4; j++) {
+    A[2 * 4 + j] = Hi00 * dr0[j] + Hi01 * dr1[j];
+    A[3 * 4 + j] = Hi01 * dr0[j] + Hi11 * dr1[j];
+  }
+  Bm[0] = 0.0;
+  Bm[1] = 0.0;
+  Bm[2] = Hi01;
+  Bm[3] = Hi11;
+}
+static void di_dynamics_jac(double *A, double *Bm) {
+  const double mass = 1.0;
+  for (int i = 0; i < 16; i++) A[i] = 0.0;
+  for (int i = 0; i < 8; i++) Bm[i] = 0.0;
+  A[0 * 4 + 2] = 1.0;
+  A[1 * 4 + 3] = 1.0;
+  Bm[2 * 2 + 0] = 1.0 / mass;
+  Bm[3 * 2 + 1] = 1.0 / mass;
+}
+
 static void model_dynamics(const orc_solver *s, const double *x, const double *u, double *dx) {
   if (s->d.model_id == ILQR_MODEL_ACROBOT) acrobot_dynamics(x, u, dx);
   else di_dynamics(x, u, dx);
@@ -257,6 +304,16 @@ static void compute_derivatives(orc_solver *s) {
   const double eps2 = s->d.params.fd_eps; /* src/derivatives.cpp:10 */
   double zero_u[NU] = {0};
   for (int t = 0; t < T; t++) { /* fx[T], fu[T] stay zero (src/ilqr_core.cpp:38-39) */
+    if (s->d.flags & ILQR_FLAG_ANALYTIC_DYN) { /* opt-in: Jacobian of the Euler step x + dt f(x, u) in closed form */
+      double A[NX * NX], Bm[NX * NU];
+      if (s->d.model_id == ILQR_MODEL_ACROBOT) acrobot_dynamics_jac(s->xs + t * n, s->us + t * m, A, Bm);
+      else di_dynamics_jac(A, Bm);
+      for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) s->fx[(t * n + i) * n + j] = (i == j ? 1.0 : 0.0) + A[i * n + j] * s->d.dt;
+        for (int j = 0; j < m; j++) s->fu[(t * n + i) * m + j] = Bm[i * m + j] * s->d.dt;
+      }
+      continue;
+    }
     fd_jacobian_dyn(s, s->xs + t * n, s->us + t * m, s->d.dt, 0, s->fx + t * n * n);
     fd_jacobian_dyn(s, s->xs + t * n, s->us + t * m, s->d.dt, 1, s->fu + t * n * m);
   }
@@ -562,6 +619,8 @@ static double forward_pass(orc_solver *s, const double *x0, const double *u, int
         uc[j] += a;
       }
     }
+    if (s->d.flags & ILQR_FLAG_CLAMP_ROLLOUT) /* opt-in: "the right way" of :327-329, the applied control obeys the limits */
+      for (int j = 0; j < m; j++) uc[j] = clampd(uc[j], s->umin[j], s->umax[j]);
     for (int j = 0; j < m; j++) s->us[t * m + j] = uc[j];
     total += model_cost(s, xc, uc);
     double x1[NX];

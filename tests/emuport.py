@@ -80,11 +80,11 @@ class EmuSolver:
     """Same surface as oracleport.OracleSolver (Vx/Vxx: timestep 0 only)."""
 
     def __init__(self, model=abi.MODEL_ACROBOT, dt=0.02, goal=None, u_min=None, u_max=None,
-                 cost_deriv=abi.COST_FD, params=None, dtype=abi.F64, libm=False, lanes=32):
+                 cost_deriv=abi.COST_FD, params=None, dtype=abi.F64, libm=False, lanes=32, flags=0):
         self.L = lib(libm)
         self.L.emu_set_lanes(int(lanes))  # 32: one trajectory per warp; 16: two per warp; 1: the phase engine (ilqr_phases.cuh)
         self.desc = abi.make_desc(model=model, dt=dt, goal=goal, u_min=u_min, u_max=u_max, cost_deriv=cost_deriv,
-                                  params=params, dtype=dtype)
+                                  params=params, dtype=dtype, flags=flags)
         self.h = self.L.emu_new(C.byref(self.desc))
         assert self.h, "emu_new failed"
         n, m = C.c_int(), C.c_int()

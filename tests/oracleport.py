@@ -76,9 +76,9 @@ class OracleSolver:
     """Same surface as refharness.RefSolver, backed by the C restatement."""
 
     def __init__(self, model=abi.MODEL_ACROBOT, dt=0.02, goal=None, u_min=None, u_max=None,
-                 cost_deriv=abi.COST_FD, params=None):
+                 cost_deriv=abi.COST_FD, params=None, flags=0):
         self.desc = abi.make_desc(model=model, dt=dt, goal=goal, u_min=u_min, u_max=u_max, cost_deriv=cost_deriv,
-                                  params=params)
+                                  params=params, flags=flags)
         self.h = lib().orc_new(C.byref(self.desc))
         assert self.h, "orc_new failed"
         n, m = C.c_int(), C.c_int()

@@ -136,6 +136,46 @@ def test_sixteen_lane_decomposition_batch_of_64():
             assert np.array_equal(a.get(f), c.get(f)) and np.array_equal(a.get(f), d.get(f)), (b, f)
 
 
+@pytest.mark.parametrize("lanes", [32, 1])
+@pytest.mark.parametrize("case,model,flags,kw", [
+    ("acrobot_lim15_T200_b0", abi.MODEL_ACROBOT, abi.FLAG_CLAMP_ROLLOUT, dict(u_min=[-1.5], u_max=[1.5])),
+    ("acrobot_T200_b1", abi.MODEL_ACROBOT, abi.FLAG_ANALYTIC_DYN, {}),
+    ("acrobot_lim15_T200_b2", abi.MODEL_ACROBOT, abi.FLAG_ANALYTIC_DYN | abi.FLAG_CLAMP_ROLLOUT, dict(u_min=[-1.5], u_max=[1.5])),
+    ("integrator_rand_T60_b1", abi.MODEL_DOUBLE_INTEGRATOR, abi.FLAG_ANALYTIC_DYN | abi.FLAG_CLAMP_ROLLOUT, None)])
+def test_opt_in_modes_kernel_source_equals_oracle(golden_solver, case, model, flags, kw, lanes):
+    """SURVEY §8 (f4), both OFF by default: rollouts that clamp the applied control (the reference's commented-out
+    "right way", src/ilqr_core.cpp:322-329) and closed-form dynamics Jacobians (notes.md:15,45).  The kernel source (warp
+    phases and phase-engine tasks) against the oracle's implementation of the same two modes, bit for bit."""
+    g = golden_solver
+    if kw is None:
+        kw = dict(goal=list(g[case + "/goal"]))
+    lockstep(model, g[case + "/x0"], g[case + "/u0"], float(g[case + "/dt"]), True, lanes=lanes, flags=flags, **kw)
+
+
+def test_opt_in_modes_do_what_they_say(golden_solver):
+    g = golden_solver
+    case = "acrobot_lim15_T200_b0"
+    kw = dict(u_min=[-1.5], u_max=[1.5])
+    a = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, **kw)
+    b = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, flags=abi.FLAG_CLAMP_ROLLOUT, **kw)
+    for o in (a, b):
+        o.init(g[case + "/x0"], g[case + "/u0"])
+        o.iterate(200)
+    assert np.abs(a.get("us")).max() > 1.5 + 1e-6 and np.abs(b.get("us")).max() <= 1.5   # default = the reference's unclamped rollouts
+    # (it does not converge better — "the wrong way, but the only way that works right now", src/ilqr_core.cpp:322 — which
+    # is why it stays an option; its cost is the cost of controls inside the limits)
+    assert np.isfinite(b.cost) and b.count("status") != 0
+    # closed-form Jacobians agree with the central differences to their O(eps^2) truncation error
+    c = O.OracleSolver(abi.MODEL_ACROBOT, 0.02)
+    d = O.OracleSolver(abi.MODEL_ACROBOT, 0.02, flags=abi.FLAG_ANALYTIC_DYN)
+    x0, u0 = g["acrobot_T200_b3/x0"], g["acrobot_T200_b3/u0"]
+    for o in (c, d):
+        o.init(x0, u0)
+        o.backward_once(1.0)
+    assert np.abs(c.get("fx") - d.get("fx")).max() < 2e-6 and np.abs(c.get("fu") - d.get("fu")).max() < 2e-6
+    assert np.abs(c.get("fx") - d.get("fx")).max() > 1e-12                                 # and are not the same numbers
+
+
 def test_warm_start_kernel_source_equals_oracle():
     rng = np.random.default_rng(3)
     x0, u0 = rng.uniform(-1, 1, 4), 0.5 * rng.uniform(-1, 1, (90, 1))
