@@ -23,6 +23,12 @@ int main(int argc, char **argv) {
   }
   iLQR solver(new Acrobot(), 0.02);
   solver.quiet = true;
+  if (const char *e = getenv("ILQR_DEMO_DEVICES")) /* e.g. "0,1": shard the batch over these GPUs (iLQR::devices) */
+    for (const char *p = e; *p;) {
+      solver.devices.push_back(atoi(p));
+      while (*p && *p != ',') p++;
+      if (*p == ',') p++;
+    }
   std::vector<double> cost = solver.solve_batch(X0, U0);
   for (int b = 0; b < B && b < 6; b++) printf("batch %d cost %.12f iterations %d\n", b, cost[b], solver.batch_iterations(b));
   if (argc > 3) {

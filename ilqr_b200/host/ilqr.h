@@ -91,6 +91,9 @@ class iLQR {
   bool quiet = false; /* the reference prints a progress table; here only the banner lines survive */
   int cost_deriv = 0; /* ILQR_COST_FD (the reference's behaviour) | ILQR_COST_ANALYTIC */
   int flags = 0;      /* ILQR_FLAG_* of include/ilqr_b200.h; 0 = the reference's behaviour */
+  /* solve_batch: CUDA ordinals to shard the batch over (contiguous blocks, one handle and one host thread per device,
+   * one ncclAllGather of the final costs: batch_solver.h).  Empty = device 0 alone through the plain handle. */
+  std::vector<int> devices;
 
  private:
   void create(long B, int T_);
@@ -108,6 +111,10 @@ class iLQR {
   std::vector<double> bxs, bus;
   std::vector<int> batch_iters, batch_status;
   std::vector<double> batch_cost;
+  class BatchSolver *multi = nullptr; /* the sharded path of solve_batch */
+  std::vector<int> multi_devices;
+  long multi_B = 0;
+  int multi_T = 0;
 };
 
 #endif

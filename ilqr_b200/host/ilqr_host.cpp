@@ -22,6 +22,7 @@
 
 #include "../../include/ilqr_b200.h"
 #include "../csrc/models.cuh"  // host instantiation of the device twins, for the construction-time check
+#include "batch_solver.h"
 #include "ilqr.h"
 
 #include <map>
@@ -148,7 +149,10 @@ void iLQR::register_device_twin(const std::type_info &type, const char *struct_n
   user_twins()[std::type_index(type)] = t; /* n, m and the limits are the object's: registration with the library happens at first construction */
 }
 
-iLQR::~iLQR() { ilqr_destroy(h); }
+iLQR::~iLQR() {
+  ilqr_destroy(h);
+  delete multi;
+}
 
 void iLQR::create(long B, int T_) {
   ilqr_desc d;
@@ -318,7 +322,6 @@ std::vector<double> iLQR::solve_batch(const std::vector<VectorXd> &X0, const std
   if (B == 0 || U0.size() != X0.size()) throw std::runtime_error("iLQR::solve_batch: X0 and U0 must have the same non-zero length");
   const int n = model->x_dims, m = model->u_dims;
   T = (int)U0[0].size();
-  create(B, T);
   std::vector<double> x0((size_t)B * n), u0((size_t)B * T * m);
   for (long b = 0; b < B; b++) {
     if ((int)U0[b].size() != T) throw std::runtime_error("iLQR::solve_batch: ragged horizons");
@@ -326,6 +329,44 @@ std::vector<double> iLQR::solve_batch(const std::vector<VectorXd> &X0, const std
     for (int t = 0; t < T; t++)
       for (int j = 0; j < m; j++) u0[((size_t)b * T + t) * m + j] = U0[b][t](j);
   }
+  if (!devices.empty()) { /* sharded over several GPUs from this one process (batch_solver.h) */
+    ilqr_desc d;
+    memset(&d, 0, sizeof(d));
+    d.model_id = model_id;
+    d.dtype = ILQR_F64;
+    d.cost_deriv = cost_deriv;
+    d.T = T;
+    d.dt = dt;
+    d.override_limits = 1;
+    for (int j = 0; j < m; j++) {
+      d.u_min[j] = model->u_min(j);
+      d.u_max[j] = model->u_max(j);
+    }
+    for (int i = 0; i < 16; i++) d.model_params[i] = model_params[i];
+    ilqr_default_params(&d.params);
+    d.params.max_iter = maxIter;
+    d.flags = flags;
+    if (!multi || multi_devices != devices || multi_T != T || memcmp(&d, &hdesc, sizeof(d)) != 0) {
+      delete multi;
+      multi = new BatchSolver(d, devices);
+      multi_devices = devices;
+      multi_T = T;
+      hdesc = d;
+    }
+    std::vector<double> cost(B);
+    std::vector<int32_t> iters(B), stat(B);
+    multi->solve(x0.data(), u0.data(), B, cost.data(), iters.data());
+    bxs.resize((size_t)B * (T + 1) * n);
+    bus.resize((size_t)B * T * m);
+    multi->get(ILQR_F_XS, bxs.data());
+    multi->get(ILQR_F_US, bus.data());
+    multi->get(ILQR_F_STATUS, stat.data());
+    batch_iters.assign(iters.begin(), iters.end());
+    batch_status.assign(stat.begin(), stat.end());
+    batch_cost = cost;
+    return cost;
+  }
+  create(B, T);
   check(ilqr_set_initial(h, x0.data(), u0.data(), 0), h, "ilqr_set_initial");
   check(ilqr_solve(h), h, "ilqr_solve");
   std::vector<double> cost(B);
