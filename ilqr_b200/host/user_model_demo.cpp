@@ -1,6 +1,6 @@
 // user_model_demo.cpp — the reference's plugin surface with a model of the user's own:
 //   user_model_demo <twin.cu> [T]
-// `class Pendulum : public Model` is what a user of the reference writes (include/model.h:6-21: dynamics, cost,
+// `class Pendulum : public Model` (pendulum_model.h) is what a user of the reference writes (include/model.h:6-21: dynamics, cost,
 // final_cost, u_min / u_max, x_dims / u_dims).  Its device twin — the same three functions as a CUDA struct, read
 // here from the file given on the command line — is registered once; `new iLQR(new Pendulum, dt)` then runs on the
 // GPU, after checking the twin against the host object.
@@ -14,33 +14,7 @@
 #include "model.h"
 #include "ilqr.h"
 
-class Pendulum : public Model {
- public:
-  Pendulum() {
-    x_dims = 2;
-    u_dims = 1;
-    u_min.resize(1);
-    u_max.resize(1);
-    u_min << -2.0;
-    u_max << 2.0;
-  }
-  double goal = 3.141592653589793;
-  virtual VectorXd dynamics(const VectorXd &x, const VectorXd &u) {
-    const double g = 9.81, l = 1, mass = 1, damping = 0.1;
-    VectorXd dx(2);
-    dx(0) = x(1);
-    dx(1) = (u(0) - damping * x(1) - mass * g * l * sin(x(0))) / (mass * l * l);
-    return dx;
-  }
-  virtual double cost(const VectorXd &x, const VectorXd &u) {
-    const double e = goal - x(0);
-    return 0.01 * (e * e) + 0.001 * (x(1) * x(1)) + 0.05 * (u(0) * u(0));
-  }
-  virtual double final_cost(const VectorXd &x) {
-    const double e = goal - x(0);
-    return 100 * (e * e) + 10 * (x(1) * x(1));
-  }
-};
+#include "pendulum_model.h"
 
 int main(int argc, char **argv) {
   if (argc < 2) {

@@ -18,6 +18,8 @@
 #include "src/boxqp.cpp"
 #include "acrobot.h"
 #include "double_integrator.h"
+// a Model subclass of the user's own (the plugin surface, include/model.h:6-21): the reference solves it like any other
+#include "../ilqr_b200/host/pendulum_model.h"
 
 #include <fcntl.h>
 #include <random>
@@ -308,12 +310,14 @@ typedef ILQRSetup_ForwardPassTest_Test Probe;
 
 extern "C" {
 
-// model_id: 0 = Acrobot (include/acrobot.h), 1 = DoubleIntegrator(goal)
+// model_id: 0 = Acrobot (include/acrobot.h), 2 = the user-model example Pendulum(goal[0]), 1 = DoubleIntegrator(goal)
 // (include/double_integrator.h).  u_min/u_max may be NULL (keep the model's own).
 static void rebuild(RefState *s) {
   delete s->solver;  // also deletes the model it owns
   if (s->model_id == 0) {
     s->model = new Acrobot();
+  } else if (s->model_id == 2) {
+    s->model = new Pendulum(s->goal[0]);
   } else {
     VectorXd g(4);
     for (int i = 0; i < 4; i++) g(i) = s->goal[i];
@@ -334,7 +338,7 @@ void *ref_new(int model_id, const double *goal, double dt, const double *u_min, 
   s->model_id = model_id;
   s->dt = dt;
   if (goal) for (int i = 0; i < 4; i++) s->goal[i] = goal[i];
-  const int m = model_id == 0 ? 1 : 2;
+  const int m = model_id == 1 ? 2 : 1;
   if (u_min && u_max) {
     s->have_limits = true;
     for (int j = 0; j < m; j++) {

@@ -168,6 +168,17 @@ def make_solver_fixture():
         s.iterate(1000)
         d["resume_final_cost"], d["resume_trips"] = s.cost, s.count("loop_trips")
         cases["acrobot_warm_b%d" % b] = d
+    # a Model subclass of the USER's own (the plugin surface, include/model.h:6-21) solved by the reference's own iLQR
+    # class: the pendulum of ilqr_b200/host/pendulum_model.h (n = 2, m = 1).  The GPU runs its device twin
+    # (tests/user_models.py: PENDULUM, compiled at run time) against these vectors.
+    rng = np.random.default_rng(5)
+    for b in range(4):
+        T = 150
+        xp = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5)])
+        up = 0.1 * rng.standard_normal((T, 1))
+        s = R.RefSolver(R.PENDULUM, 0.05, goal=[np.pi, 0, 0, 0])
+        cases["pendulum_T150_b%d" % b] = dict(trace_instance(s, xp, up, checkpoints=(1, 5, 20)), x0=xp, u0=up, dt=0.05,
+                                              goal=np.pi)
     # keep the file small: the big per-checkpoint arrays only for a subset
     np.savez_compressed(os.path.join(HERE, "solver_golden.npz"), **pack(cases))
     return cases

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
 
 ACROBOT, DOUBLE_INTEGRATOR = 0, 1
+PENDULUM = 2  # the user-model example (ilqr_b200/host/pendulum_model.h): goal[0] = goal angle
 STATUS = {0: "RUNNING", 1: "GRAD", 2: "TOLFUN", 3: "LAMBDA_MAX", 4: "MAXITER"}
 FIELDS = dict(xs=0, us=1, K=2, k=3, cost=4, dV=5, Vx=6, Vxx=7, fx=8, fu=9, cx=10, cu=11, cxx=12, cxu=13, cuu=14)
 _dp = C.POINTER(C.c_double)

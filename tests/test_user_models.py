@@ -87,6 +87,40 @@ def test_user_pendulum_swings_up_and_closed_form_matches_finite_differences():
     assert np.allclose(a["c1"], f["c1"], rtol=1e-6)
 
 
+@pytest.mark.gpu
+def test_user_pendulum_against_the_reference_solving_the_host_model(golden_solver):
+    """SURVEY §8 (f2), oracle side: `class Pendulum : public Model` (ilqr_b200/host/pendulum_model.h, the user's HOST
+    object) was solved by the UNMODIFIED reference's own iLQR class (oracle/ref_harness.cpp takes any Model*;
+    tests/golden/make_golden.py wrote the vectors); its device twin, compiled at run time, must reproduce the reference's
+    K, k, xs, us and cost after 1 and 5 trips to 1e-6 on every instance, and the terminal cost."""
+    g = golden_solver
+    cases = ["pendulum_T150_b%d" % b for b in range(4)]
+    x0 = np.stack([g[c + "/x0"] for c in cases])
+    u0 = np.stack([g[c + "/u0"] for c in cases])
+    pid = abi.register_model("Pendulum", U.PENDULUM, 2, 1, [-2.0], [2.0])
+    s = BatchILQR(pid, T=150, B=len(cases), dt=0.05, cost_deriv=abi.COST_FD, model_params=[float(g[cases[0] + "/goal"])])
+
+    def close(a, b, rtol=1e-6, atol=1e-9):
+        a, b = np.asarray(a, float).reshape(len(cases), -1), np.asarray(b, float).reshape(len(cases), -1)
+        err = np.maximum(np.abs(a - b).max(1) - atol, 0) / np.maximum(np.abs(b).max(1), 1e-300)
+        assert (err <= rtol).all(), err
+    close(s.init_traj(x0, u0), [g[c + "/init_cost"] for c in cases], 1e-12, 0)
+    s.backward_once(1.0)
+    for f, name in (("K", "bw_K"), ("k", "bw_k"), ("dV", "bw_dV"), ("Vx0", "bw_Vx0"), ("Vxx0", "bw_Vxx0")):
+        close(s.get(f), np.stack([g[c + "/" + name] for c in cases]), 1e-7)
+    s.set_initial(x0, u0)
+    done = 0
+    for n in (1, 5):
+        s.iterate(n - done)
+        done = n
+        for f in ("K", "k", "xs", "us"):
+            close(s.get(f), np.stack([g["%s/it%d_%s" % (c, n, f)] for c in cases]))
+        close(s.get("cost"), [g["%s/it%d_cost" % (c, n)] for c in cases])
+    s.solve()
+    close(s.get("cost"), [g[c + "/final_cost"] for c in cases], 1e-5)
+    assert np.abs(s.get("iters") - np.array([int(g[c + "/final_trips"]) for c in cases])).max() <= 12
+
+
 HOST_DEMO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ilqr_b200", "host", "_build",
                          "user_model_demo")
 
