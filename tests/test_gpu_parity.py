@@ -350,8 +350,10 @@ def test_fast_fma_build_within_1e_6(model, cd, T, kw, engine_flags, handover, mo
         g = gpu_snap(s)
         assert (g["alpha_index"] == ref["alpha_index"]).mean() >= 0.98
         for f in ("cost", "lam", "xs", "us", "K", "k"):
-            close(g[f], ref[f], frac=0.98)      # measured: 128 of 128 (acrobot), 127 of 128 (double integrator, FD mode)
-            close(g[f], ref[f], rtol=1e-3)      # the straggler: 1.3e-4 (the FD cost Hessian divides rounding noise by 4 eps^2)
+            # measured: 128 of 128 (acrobot, both modes); the double integrator in FD-cost mode has ONE instance of 128
+            # that sits on a branch of the m = 2 boxQP after five trips (the FD cost Hessian divides the FMA rounding
+            # difference by 4 eps^2), every other one within 1e-6
+            close(g[f], ref[f], frac=1.0 if (n_it == 1 or model == abi.MODEL_ACROBOT) else 0.98)
     s.solve()
     assert (s.get("status") != abi.RUNNING).all()
     ref = oracle_batch(model, x0, u0, dt, 101, snap, cost_deriv=cd, **kw)
