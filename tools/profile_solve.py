@@ -18,8 +18,8 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["B"]
 n_iters = int(sys.argv[3]) if len(sys.argv) > 3 else -1
 x0, u0 = make_inputs(bench.SEED, B, cfg["T"], 4, 1)
 kw = dict(u_min=[-cfg["limits"]], u_max=[cfg["limits"]]) if cfg["limits"] else {}
-s = BatchILQR(abi.MODEL_ACROBOT, T=cfg["T"], B=B, dt=0.02,
-              cost_deriv=abi.COST_ANALYTIC if cfg["cost_deriv"] == "analytic" else abi.COST_FD, **kw)
+s = BatchILQR(abi.MODEL_ACROBOT, T=cfg["T"], B=B, dt=0.02, dtype=abi.F32 if cfg.get("dtype") == "f32" else abi.F64,
+              cost_deriv=abi.COST_ANALYTIC if cfg["cost_deriv"] == "analytic" else abi.COST_FD, flags=cfg.get("flags", 0), **kw)
 for _ in range(2):
     s.set_initial(x0, u0)
     if n_iters < 0:
