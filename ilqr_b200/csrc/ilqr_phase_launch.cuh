@@ -23,16 +23,21 @@ constexpr int kPhaseCheckEvery = 8; /* trips between read-backs of the active co
  * (2368 resident warps).  Measured on BASELINE configs[1] (gpurun_out r2h/r2i): 59.7 ms lockstep only, 48.8 ms with
  * the hand-over at 3200, 53.3 ms persistent kernel only. */
 constexpr long long kPhaseHandover = 3200;
+/* Running trajectories above which the line search stores no candidates (cost-only rollouts + one re-roll of the
+ * accepted candidate, ilqr_phases.cuh: rollout_task).  OFF by default (environment ILQR_B200_REROLL_MIN turns it on):
+ * it removes the candidate buffers (88 KB per trajectory at T = 200) and 40 % of the DRAM traffic of configs[4]
+ * (483 of 1203 GB per solve are candidate stores, ten of eleven never read), but the extra rollout — one thread per
+ * accepted trajectory, a 200-step chain at low occupancy — costs more time than the stores: configs[4] shard 11.0 ->
+ * 9.2 M it/s, configs[2] 5.7 -> 3.4 M it/s (gpurun_out/r2t).  For batches whose candidate buffers would not fit. */
+constexpr long long kPhaseRerollMin = 1LL << 62;
 
 template <class Model, typename S, int CD>
 int phase_prepare(ilqr_handle *h) {
   if (h->phReady) return ILQR_OK;
   constexpr size_t N = Model::N, M = Model::M, NM = N + M, NCF = NM + NM * NM;
-  const size_t B = (size_t)h->desc.B, T = (size_t)h->desc.T, na = (size_t)h->desc.params.n_alpha;
+  const size_t B = (size_t)h->desc.B, T = (size_t)h->desc.T;
   CU(h, cudaMalloc(&h->phF, B * T * NM * N * sizeof(S)));
   if (CD == kCostFD) CU(h, cudaMalloc(&h->phC, B * T * NCF * sizeof(S)));
-  CU(h, cudaMalloc(&h->phCandX, B * T * na * N * sizeof(S)));
-  CU(h, cudaMalloc(&h->phCandU, B * T * na * M * sizeof(S)));
   CU(h, cudaMalloc(&h->phNewcost, B * kMaxAlpha * sizeof(S)));
   CU(h, cudaMalloc(&h->phGterm, B * T * sizeof(S)));
   CU(h, cudaMalloc((void **)&h->phAct, 2 * B * sizeof(int)));
@@ -67,6 +72,7 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
   a.buf.n_act = h->phNact;
   a.B = h->desc.B;
   a.parity = 0;
+  a.reroll = 0;
   a.force_sweep = 1;
   cudaStream_t st = h->stream;
   CU(h, cudaMemsetAsync(h->phNact, 0, 2 * sizeof(int), st));
@@ -88,6 +94,10 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
   long long handover = kPhaseHandover;
   if (const char *e = getenv("ILQR_B200_HANDOVER")) handover = atoll(e);
   int check_every = h->desc.B <= 16384 ? 4 : kPhaseCheckEvery;
+  /* above this many running trajectories the line search keeps no candidates and re-rolls the accepted one
+   * (ilqr_phases.cuh: rollout_task) */
+  long long reroll_min = kPhaseRerollMin;
+  if (const char *e = getenv("ILQR_B200_REROLL_MIN")) reroll_min = atoll(e);
   if (const char *e = getenv("ILQR_B200_CHECK_EVERY")) check_every = atoi(e) > 0 ? atoi(e) : check_every;
   constexpr int N = Model::N, M = Model::M;
   const size_t pre_smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S, 32>>::Sc, S>(h->desc.T) * kWarpsPerCta;
@@ -128,9 +138,26 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
       phase_backward_kernel<Model, S, CD><<<(unsigned)((bound + kBackwardThreads - 1) / kBackwardThreads), kBackwardThreads, 0, st>>>(a);
       h->launches += 2;
     }
-    phase_rollout_kernel<Model, S, CD><<<(unsigned)((bound * na + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
+    a.reroll = bound > reroll_min;
+    if (!a.reroll && !h->phCandX) { /* the candidate buffers, on first use */
+      const size_t B = (size_t)h->desc.B, T = (size_t)h->desc.T;
+      CU(h, cudaMalloc(&h->phCandX, B * T * na * N * sizeof(S)));
+      CU(h, cudaMalloc(&h->phCandU, B * T * na * M * sizeof(S)));
+      a.buf.cand_x = (S *)h->phCandX;
+      a.buf.cand_u = (S *)h->phCandU;
+    }
+    if (a.reroll)
+      phase_rollout_kernel<Model, S, CD, Phases<Model, S, CD>::kCostOnly>
+          <<<(unsigned)((bound * na + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
+    else
+      phase_rollout_kernel<Model, S, CD, Phases<Model, S, CD>::kToCand>
+          <<<(unsigned)((bound * na + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
     phase_accept_kernel<Model, S, CD><<<(unsigned)((bound * 32 + kAcceptThreads - 1) / kAcceptThreads), kAcceptThreads, 0, st>>>(a);
     h->launches += 2;
+    if (a.reroll) {
+      phase_commit_kernel<Model, S, CD><<<(unsigned)((bound + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
+      h->launches += 1;
+    }
     if ((trip + 1) % check_every == 0) {
       if (pending >= 0) { /* the count of kPhaseCheckEvery trips ago: by now it has almost always arrived */
         CU(h, cudaEventSynchronize(h->phEvent[pending]));

@@ -28,8 +28,9 @@
  * the oracle.
  *
  * HBM (per handle, all per TRAJECTORY): F [B][T][n+m][n] Jacobian columns, C [B][T][NCF] (FD-cost mode),
- * cand_x [B][T][n_alpha][n], cand_u [B][T][n_alpha][m] (candidate-interleaved: the n_alpha stores of one timestep
- * are contiguous), newcost [B][16], act [2][B] active lists.
+ * cand_x [B][T][n_alpha][n], cand_u [B][T][n_alpha][m] (candidate-interleaved: the n_alpha stores of one timestep are
+ * contiguous — with every candidate's block contiguous instead, each store instruction touched eleven DRAM pages and
+ * configs[4] lost a quarter of its rate), newcost [B][16], act [2][B] active lists.
  */
 #ifndef ILQR_PHASES_CUH_
 #define ILQR_PHASES_CUH_
@@ -138,7 +139,7 @@ template <typename S>
 struct PhaseBufs {
   S *F;       /* [B][T][n+m][n]      */
   S *C;       /* [B][T][NCF]         FD-cost mode only */
-  S *cand_x;  /* [B][T][n_alpha][n]  candidate states x_1..x_T */
+  S *cand_x;  /* [B][T][n_alpha][n]  candidate states x_1..x_T (allocated on first use: not needed in re-roll mode) */
   S *cand_u;  /* [B][T][n_alpha][m]  candidate controls */
   S *newcost; /* [B][kMaxAlpha]      */
   S *gterm;   /* [B][T]              per-timestep terms of the gradient norm, written by the backward phase */
@@ -517,9 +518,19 @@ struct Phases {
 
   /* iLQR::forward_pass (:305-337) for candidate `a` of the line search (:188-197): u_t = us_t + alpha k_t +
    * K_t (x_t - xs_t), unclamped; controls and states stream to the trajectory's candidate buffer, the cost is
-   * returned.  cand_x / cand_u point at the trajectory's [T][na][.] block. */
+   * returned.  Where the rollout goes (MODE):
+   *   kToCand    to the trajectory's candidate buffer (cand_x / cand_u = its [T][n_alpha][.] block);
+   *   kCostOnly  nowhere — only the cost is wanted;
+   *   kInPlace   over xs[1..T] / us themselves: the commit of an accepted candidate by re-rolling it (the nominal
+   *              x_{t+1}, u_{t+1} are in registers before the step overwrites them).
+   * Small active sets keep every candidate (kToCand) and commit by a copy: a round of launches costs its latency
+   * floor and a second rollout would add to it.  Large ones are throughput- and HBM-bound — the candidates were 40 %
+   * of all DRAM traffic of configs[4] and ten of eleven are never read — so they run kCostOnly and re-roll the one
+   * accepted candidate (one extra rollout in eleven; same operations, same bits). */
+  enum { kToCand = 0, kCostOnly = 1, kInPlace = 2 };
+  template <int MODE>
   ILQR_HD static S rollout_task(const SolveParams<S> &P, const TrajPtrs<S> &tr, S *cand_x, S *cand_u, int a) {
-    const int T = P.T, na = P.n_alpha;
+    const int T = P.T;
     const S alpha = P.alpha[a];
     const S *mp = P.mp;
     S x[N], cost = 0;
@@ -561,8 +572,13 @@ struct Phases {
       integrate<Model, S>(x, uc, mp, P.dt, x1); /* :325 */
 #pragma unroll
       for (int i = 0; i < N; i++) x[i] = x1[i];
-      store_run<M>(cand_u + ((size_t)t * na + a) * M, uc);
-      store_run<N>(cand_x + ((size_t)t * na + a) * N, x);
+      if constexpr (MODE == kToCand) {
+        store_run<M>(cand_u + ((size_t)t * P.n_alpha + a) * M, uc);
+        store_run<N>(cand_x + ((size_t)t * P.n_alpha + a) * N, x);
+      } else if constexpr (MODE == kInPlace) {
+        store_run<M>(tr.us + (size_t)t * M, uc);
+        store_run<N>(tr.xs + (size_t)(t + 1) * N, x);
+      }
     }
     cost += Model::final_cost(x, mp); /* :335 */
     return cost;
@@ -641,6 +657,7 @@ struct PArgs {
   long long B;
   int parity;      /* which active list this trip reads */
   int force_sweep; /* first trip of an ilqr_iterate call: F / C may be stale (set_initial, warm start, test hooks) */
+  int reroll;      /* this trip's line search keeps no candidates: the accepted one is re-rolled (phase_commit_kernel) */
 };
 
 template <typename S>
@@ -1157,7 +1174,7 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) phase_pre_warp_kern
 #define ILQR_ROLLOUT_MINB 1
 #endif
 constexpr int kRolloutThreads = ILQR_ROLLOUT_THREADS;
-template <class Model, typename S, int CD>
+template <class Model, typename S, int CD, int MODE>
 __global__ void __launch_bounds__(kRolloutThreads, ILQR_ROLLOUT_MINB) phase_rollout_kernel(const __grid_constant__ PArgs<S> a) {
   using Ph = Phases<Model, S, CD>;
   constexpr int N = Model::N, M = Model::M;
@@ -1171,8 +1188,27 @@ __global__ void __launch_bounds__(kRolloutThreads, ILQR_ROLLOUT_MINB) phase_roll
   if (a.st[b].roll != kRollGo) return;
   const TrajPtrs<S> tr = phase_pointers(a, b, N, M);
   const size_t T = (size_t)a.P.T;
-  const S c = Ph::rollout_task(a.P, tr, a.buf.cand_x + b * T * na * N, a.buf.cand_u + b * T * na * M, cand);
+  /* MODE is a template parameter: with both variants behind a run-time branch the kernel carried two copies of the hot
+   * loop and configs[4] lost 20 % */
+  const S c = Ph::template rollout_task<MODE>(a.P, tr, MODE == Ph::kToCand ? a.buf.cand_x + b * T * na * N : nullptr,
+                                              MODE == Ph::kToCand ? a.buf.cand_u + b * T * na * M : nullptr, cand);
   a.buf.newcost[b * kMaxAlpha + cand] = c;
+}
+
+/* re-roll mode: the accepted candidate of every trajectory that took a step this trip, rolled out once more over
+ * xs / us (one thread per trajectory; runs after the accept phase, which has recorded alpha_index) */
+template <class Model, typename S, int CD>
+__global__ void __launch_bounds__(kRolloutThreads, ILQR_ROLLOUT_MINB) phase_commit_kernel(const __grid_constant__ PArgs<S> a) {
+  using Ph = Phases<Model, S, CD>;
+  constexpr int N = Model::N, M = Model::M;
+  const int n_act = a.buf.n_act[a.parity];
+  const long long i = blockIdx.x * (long long)kRolloutThreads + threadIdx.x;
+  if (i >= n_act) return;
+  const long long b = a.buf.act[(size_t)a.parity * a.B + i];
+  const TrajState<S> &s = a.st[b];
+  if (s.roll != kRollGo || s.alpha_index < 0) return; /* no line search this trip, or no step taken */
+  const TrajPtrs<S> tr = phase_pointers(a, b, N, M);
+  Ph::template rollout_task<Ph::kInPlace>(a.P, tr, nullptr, nullptr, s.alpha_index);
 }
 
 constexpr int kAcceptThreads = 128;
@@ -1198,7 +1234,7 @@ __global__ void __launch_bounds__(kAcceptThreads) phase_accept_kernel(const __gr
       if (go_on) a.buf.act[(size_t)(a.parity ^ 1) * a.B + atomicAdd(&a.buf.n_act[a.parity ^ 1], 1)] = (int)b;
     }
     code = __shfl_sync(0xffffffffu, code, 0);
-    if (code & 1) { /* xs[1..T], us[0..T-1] <- the accepted candidate (what forward_pass left, :323,334) */
+    if ((code & 1) && !a.reroll) { /* xs[1..T], us[0..T-1] <- the accepted candidate (what forward_pass left, :323,334) */
       const int ai = code >> 8;
       const S *cx = a.buf.cand_x + b * T * na * N;
       const S *cu = a.buf.cand_u + b * T * na * M;

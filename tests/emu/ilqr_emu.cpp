@@ -127,15 +127,22 @@ struct Emu : EmuBase {
             for (int t = 0; t < T; t++) Ph::stencil_task(P, xs.data(), us.data(), bufC.data(), o, t);
       }
       Ph::backward_trip(P, tr, bufF.data(), bufC.data(), gterm.data(), st, 1u);
+      const bool reroll = (trip & 1) != 0; /* alternate the two line-search modes: both must give the oracle's bits */
       if (st.roll == kRollGo)
-        for (int a = 0; a < na; a++) newcost[a] = Ph::rollout_task(P, tr, candX.data(), candU.data(), a);
+        for (int a = 0; a < na; a++)
+          newcost[a] = reroll ? Ph::template rollout_task<Ph::kCostOnly>(P, tr, nullptr, nullptr, a)
+                              : Ph::template rollout_task<Ph::kToCand>(P, tr, candX.data(), candU.data(), a);
       if (st.status != kRunning) break;
       const bool fwd = Ph::accept(P, st, newcost);
       if (fwd) {
         const int ai = st.alpha_index;
-        for (int t = 0; t < T; t++) {
-          for (int c = 0; c < N; c++) xs[(size_t)(t + 1) * N + c] = candX[((size_t)t * na + ai) * N + c];
-          for (int c = 0; c < M; c++) us[(size_t)t * M + c] = candU[((size_t)t * na + ai) * M + c];
+        if (reroll) {
+          Ph::template rollout_task<Ph::kInPlace>(P, tr, nullptr, nullptr, ai);
+        } else {
+          for (int t = 0; t < T; t++) {
+            for (int c = 0; c < N; c++) xs[(size_t)(t + 1) * N + c] = candX[((size_t)t * na + ai) * N + c];
+            for (int c = 0; c < M; c++) us[(size_t)t * M + c] = candU[((size_t)t * na + ai) * M + c];
+          }
         }
       }
       run = Ph::schedule(P, st, fwd);

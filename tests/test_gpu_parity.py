@@ -305,6 +305,34 @@ def test_sixteen_lane_kernel_batch(model, cd, dtype, T, kw, monkeypatch):
             assert np.array_equal(ref.get(f), s16.get(f)), (n_it, f)
 
 
+@pytest.mark.parametrize("model,cd,dtype,T,kw", [
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F64, 200, {}),
+    (abi.MODEL_ACROBOT, abi.COST_FD, abi.F64, 120, dict(u_min=[-1.5], u_max=[1.5])),
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F32, 300, {}),
+    (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, abi.F64, 60, dict(goal=[1.0, 1.0, 0.0, 0.0])),
+])
+@pytest.mark.parametrize("head", ["rows", "thread"])
+def test_phase_engine_reroll_mode(model, cd, dtype, T, kw, head, monkeypatch):
+    """the line search of large active sets: cost-only candidate rollouts, then ONE re-roll of the accepted candidate over
+    xs / us (ilqr_phases.cuh: rollout_task kCostOnly / kInPlace) instead of eleven stored candidates and a copy.  Same
+    operations, so the same bits as the store-all mode and as the warp engine, switching modes in mid-solve included."""
+    B = 200
+    n, m = abi.MODEL_DIMS[model]
+    x0, u0 = make_inputs(808, B, T, n, m)
+    dt = 0.02 if model == abi.MODEL_ACROBOT else 0.05
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")
+    monkeypatch.setenv("ILQR_B200_ROWS_MAX", "0" if head == "thread" else "1000000")
+    ref = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, flags=abi.FLAG_ENGINE_WARP, **kw)
+    ref.generate_trajectory(x0, u0)
+    for reroll_min, check in (("0", "8"), ("120", "1")):      # always re-roll; re-roll until 120 are left, then store-all
+        monkeypatch.setenv("ILQR_B200_REROLL_MIN", reroll_min)
+        monkeypatch.setenv("ILQR_B200_CHECK_EVERY", check)
+        s = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, **kw)
+        s.generate_trajectory(x0, u0)
+        for f in ALL_FIELDS:
+            assert np.array_equal(s.get(f), ref.get(f)), (reroll_min, f)
+
+
 @pytest.mark.parametrize("handover,check", [(150, 1), (250, 3), (40, 8)])
 def test_phase_engine_hands_the_tail_to_the_persistent_kernel(handover, check, monkeypatch):
     """lockstep rounds while many trajectories run, then the persistent warp kernel for the survivors' remaining trips
