@@ -723,8 +723,11 @@ __global__ void __launch_bounds__(kSweepThreads) phase_sweep_kernel(const __grid
 }
 
 constexpr int kBackwardThreads = 32;
+#ifndef ILQR_BACKWARD_MINB
+#define ILQR_BACKWARD_MINB 1
+#endif
 template <class Model, typename S, int CD>
-__global__ void __launch_bounds__(kBackwardThreads) phase_backward_kernel(const __grid_constant__ PArgs<S> a) {
+__global__ void __launch_bounds__(kBackwardThreads, ILQR_BACKWARD_MINB) phase_backward_kernel(const __grid_constant__ PArgs<S> a) {
   using Ph = Phases<Model, S, CD>;
   constexpr int N = Model::N, M = Model::M, NM = N + M;
   const int n_act = a.buf.n_act[a.parity];
