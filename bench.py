@@ -12,12 +12,19 @@ executed, summed over the batch, per second.
   value  inputs already resident in HBM; timed with CUDA events on the library's stream.
   e2e    the same through the C ABI with HOST buffers: pinned x0/u0 -> H2D -> solve -> D2H of the
          final costs and trip counts, copies inside the timed region.
-  roofline  the solve kernel alone: ALGORITHMIC bytes (40 096 B per accepted and
+  roofline  one ilqr_solve (all its kernels): ALGORITHMIC bytes (40 096 B per accepted and
          32 064 B per rejected trip at n=4, m=1, T=200, f64) / its CUDA-event duration, against the
-         measured HBM copy bandwidth in MEASURED_PEAKS.json.
+         measured HBM copy bandwidth in MEASURED_PEAKS.json; `traffic` = DRAM bytes of one solve from the
+         committed ncu counters (profiles/traffic.json).  `secondary` = the ceiling that actually binds:
+         useful flops against the fp64 issue rate measured on this GPU (ilqr_measure_fp64),
+         with warp instructions per trip / lanes per instruction from the same ncu capture.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/libref_oracle.so, built from /root/reference
          by oracle/Makefile) on the host cores, one forked worker per core, on a bounded sample of
-         the same batch.
+         the same batch; `terminal_cost_vs_gpu` compares the two on that sample, and `like_for_like`
+         repeats it with the GPU in the reference's own derivative mode (finite-difference costs) plus
+         K, k, cost after 5 trips.
+  extras  (default line only) short runs of BASELINE configs[2], [3], the configs[4] shard and the opt-in
+         FMA build, each with its rate, exit-status histogram and a parity sample against the reference.
 
 N > 1 (torchrun, one rank per GPU): every rank solves its own B instances (weak scaling, no
 data-path collective) and the final costs are gathered to rank 0 with ONE NCCL gather per step.

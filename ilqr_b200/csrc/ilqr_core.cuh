@@ -870,6 +870,7 @@ struct Core {
       sc.st.dV0 = L.dV[0];
       sc.st.dV1 = L.dV[1];
     });
+    pass_complete = diverged_at < 0;
     if (diverged_at >= 0) return diverged_at;
     /* Vx[0], Vxx[0] are results of record for the tests (include/ilqr.h:76-77) */
     ex.lanes([&](int lane, Lane &) {
@@ -1138,7 +1139,7 @@ struct Core {
       sc.st.lam = lam;
       sc.st.diverge = d;
     });
-    if (d == 0) gradient_norm_from_terms();
+    if (d == 0 && pass_complete) gradient_norm_from_terms();
     else gradient_norm_only();
     store_state();
   }
@@ -1156,6 +1157,10 @@ struct Core {
    * carrying two trajectories can advance both one trip at a time in lockstep:
    *   iterate_begin(n);  while (iterate_trip()) {}  iterate_end();                                      */
   int trips_left = 0;
+  /* the last backward pass ran every timestep.  A pass that stops at timestep 0 returns 0 like a success (:371 vs :142)
+   * but has not written this pass's gradient-norm term of timestep 0: the norm is then formed from k and us as they
+   * stand (the stale k[0] with the current us[0], like the reference's get_gradient_norm) */
+  bool pass_complete = false;
   bool have_derivs = false; /* the lane group's F / C buffers hold this trajectory's current derivatives */
 
   ILQR_HD void iterate_begin(int n_iters) {
@@ -1218,7 +1223,7 @@ struct Core {
       }
       back_done = true;
     }
-    if (back_done) gradient_norm_from_terms();
+    if (back_done && pass_complete) gradient_norm_from_terms();
     else gradient_norm_only();
     /* :153-159 */
     ex.lanes([&](int lane, Lane &) {
