@@ -14,6 +14,16 @@
 #include "batch_solver.h"
 
 int main(int argc, char **argv) {
+  if (argc > 1 && strcmp(argv[1], "--shards") == 0) { /* bench_batch --shards TOTAL WORLD: the partition, no GPU needed */
+    const long total = argc > 2 ? atol(argv[2]) : 0;
+    const int world = argc > 3 ? atoi(argv[3]) : 1;
+    for (int r = 0; r < world; r++) {
+      long lo, hi;
+      BatchSolver::shard_bounds(total, world, r, &lo, &hi);
+      printf("%ld %ld\n", lo, hi);
+    }
+    return 0;
+  }
   try {
     ilqr_desc d;
     memset(&d, 0, sizeof(d));

@@ -69,3 +69,20 @@ def test_gather_of_final_costs_world2_gloo():
 def test_single_process_is_identity():
     x = torch.arange(4, dtype=torch.float64)
     assert shard.gather_final_costs(x) is x
+
+
+def test_cpp_host_partition_equals_python_partition():
+    """BatchSolver::shard_bounds (ilqr_b200/host/batch_solver.cpp, the one-process multi-GPU host path) cuts a batch into
+    the same contiguous blocks as shard.shard_bounds (the torchrun path)"""
+    import os
+    import subprocess
+    from ilqr_b200 import shard
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ilqr_b200", "host", "_build", "bench_batch")
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("host binaries not built")
+    for total, world in ((1048576, 8), (4096, 3), (7, 8), (100, 1)):
+        out = subprocess.run([exe, "--shards", str(total), str(world)], capture_output=True, text=True, check=True).stdout.split()
+        got = [(int(out[2 * r]), int(out[2 * r + 1])) for r in range(world)]
+        assert got == [shard.shard_bounds(total, world, r) for r in range(world)]
+        assert got[0][0] == 0 and got[-1][1] == total
