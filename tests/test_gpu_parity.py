@@ -856,6 +856,32 @@ def test_edge_shapes_bit_exact(model, T, B, dt):
             assert np.array_equal(np.asarray(g[f][b]), np.asarray(r[f])), (b, f)
 
 
+@pytest.mark.parametrize("head", ["rows", "thread", "warp"])
+@pytest.mark.parametrize("model,T,B,dt", [(abi.MODEL_ACROBOT, 1, 1, 0.02), (abi.MODEL_ACROBOT, 2, 5, 0.02), (abi.MODEL_ACROBOT, 9, 33, 0.05),
+                                          (abi.MODEL_DOUBLE_INTEGRATOR, 1, 2, 0.05), (abi.MODEL_DOUBLE_INTEGRATOR, 7, 35, 0.1)])
+def test_edge_shapes_phase_engine_bit_exact(model, T, B, dt, head, monkeypatch):
+    """horizons of one and two timesteps, batches that do not fill a warp / a lane group / a CTA, forced through the
+    lockstep phase kernels (a batch this small normally goes straight to the persistent kernel): GPU == kernel source on
+    the CPU, bit for bit, both derivative modes"""
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")
+    monkeypatch.setenv("ILQR_B200_ROWS_MAX", "0" if head == "thread" else "1000000")
+    monkeypatch.setenv("ILQR_B200_WARP_PRE_MAX", "1000000" if head == "warp" else "0")
+    n, m = abi.MODEL_DIMS[model]
+    x0, u0 = make_inputs(77, B, T, n, m, canonical_first=False)
+    kw = dict(goal=[0.5, -0.5, 0.0, 0.0]) if model == abi.MODEL_DOUBLE_INTEGRATOR else {}
+    for cd in (abi.COST_FD, abi.COST_ANALYTIC):
+        s = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, **kw)
+        s.generate_trajectory(x0, u0)
+        g = gpu_snap(s)
+        for b in range(min(B, 6)):
+            e = E.EmuSolver(model, dt, cost_deriv=cd, **kw)
+            e.init(x0[b], u0[b])
+            e.iterate(1000)
+            r = snap(e)
+            for f in g:
+                assert np.array_equal(np.asarray(g[f][b]), np.asarray(r[f])), (cd, b, f)
+
+
 @pytest.mark.parametrize("T", [37, 38, 199, 200])
 @pytest.mark.parametrize("lanes", ["32", "16"])
 def test_shared_memory_layout_odd_and_even_horizons(T, lanes, monkeypatch):
