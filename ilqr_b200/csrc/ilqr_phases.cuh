@@ -761,6 +761,9 @@ __device__ __forceinline__ S cost_d2_rt(int c, int d, const S *x, const S *u, co
  * the one-thread-per-trajectory kernel's and the instruction count per trajectory a fifth of the 32-lane
  * decomposition's, which is what a batch of a few thousand trajectories (BASELINE configs[1]) needs: too few to
  * fill the machine one thread each, too many to give each a warp.  Same expressions, same bits. */
+#if defined(ILQR_ROWS_CLOCKS)
+static __device__ unsigned long long g_rows_clk[4] = {0, 0, 0, ~0ULL};
+#endif
 constexpr int kRowLanes = 8;
 constexpr int kRowThreads = 128;
 template <class Model, typename S, int CD>
@@ -798,6 +801,9 @@ __global__ void __launch_bounds__(kRowThreads, 2) phase_backward_rows_kernel(con
    * and the warp issued four streams in turn: ncu 15 threads per instruction, 3.6 k cycles per timestep.) */
   const unsigned gmask = __ballot_sync(0xffffffffu, i < n_act);
   if (i >= n_act) return;
+#if defined(ILQR_ROWS_CLOCKS)
+  const long long rows_t0 = clock64();
+#endif
   const long long b = a.buf.act[(size_t)a.parity * a.B + i];
   const TrajPtrs<S> tr = phase_pointers(a, b, N, M);
   const SolveParams<S> &P = a.P;
@@ -1113,6 +1119,23 @@ __global__ void __launch_bounds__(kRowThreads, 2) phase_backward_rows_kernel(con
     }
     __syncwarp(gmask);
   }
+#if defined(ILQR_ROWS_CLOCKS) /* experiment builds: spread of the per-warp durations of this launch */
+  if (wl == 0) {
+    const unsigned long long dt = (unsigned long long)(clock64() - rows_t0);
+    atomicAdd(&g_rows_clk[0], dt);
+    atomicMax(&g_rows_clk[1], dt);
+    atomicMin(&g_rows_clk[3], dt);
+    const unsigned long long done = atomicAdd(&g_rows_clk[2], 1ULL) + 1;
+    const unsigned long long total = ((unsigned long long)n_act + kPerCta - 1) / kPerCta * (kRowThreads / 32) -
+                                     ((unsigned long long)(((n_act + kPerCta - 1) / kPerCta) * kPerCta - n_act) / GPW);
+    if (done == total) {
+      printf("rows launch: %llu warps, mean %.0f cycles, min %llu, max %llu (n_act %d)\n", done, (double)g_rows_clk[0] / done,
+             g_rows_clk[3], g_rows_clk[1], n_act);
+      g_rows_clk[0] = g_rows_clk[1] = g_rows_clk[2] = 0;
+      g_rows_clk[3] = ~0ULL;
+    }
+  }
+#endif
   if (qp_lane) {
     __threadfence_block(); /* K / k were written by this lane; the reads below are its own */
     s.gnorm = (back_done && complete) ? Ph::gradient_norm_terms(P, gterm) : Ph::gradient_norm(P, tr);
