@@ -555,6 +555,16 @@ def ours_arm(args, cfg):
                 line["cpu_baseline"]["like_for_like"] = like_for_like(cfg, B, r.x0, r.u0, n_sample, cores, local)
             except Exception as e:  # never lose the headline to the checker
                 line["cpu_baseline"]["like_for_like"] = {"error": repr(e)}
+        # the same workload through the C++ host layer (one process, BatchSolver: pinned inputs, one ncclAllGather), end to end
+        cpp = os.path.join(ROOT, "ilqr_b200", "host", "_build", "bench_batch")
+        if world == 1 and os.path.exists(cpp) and cfg["cost_deriv"] == "analytic" and not cfg["limits"] and not r.f32:
+            try:
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))
+                out = subprocess.run([cpp, str(B), str(T), "3", "2"], capture_output=True, text=True, timeout=600, env=env)
+                last = [l for l in out.stdout.strip().split("\n") if l.startswith("{")][-1]
+                line["e2e_cpp_host"] = json.loads(last)
+            except Exception as e:
+                line["e2e_cpp_host"] = {"error": repr(e)}
         if world == 1 and not args.no_extras and args.config == "cfg2" and not args.batch:
             del r, solver
             line["extras"] = {}
