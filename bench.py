@@ -559,7 +559,8 @@ def ours_arm(args, cfg):
         cpp = os.path.join(ROOT, "ilqr_b200", "host", "_build", "bench_batch")
         if world == 1 and os.path.exists(cpp) and cfg["cost_deriv"] == "analytic" and not cfg["limits"] and not r.f32:
             try:
-                env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))
+                vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v]
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES=vis[local] if local < len(vis) else str(local))  # this rank's GPU only
                 out = subprocess.run([cpp, str(B), str(T), "3", "2"], capture_output=True, text=True, timeout=600, env=env)
                 last = [l for l in out.stdout.strip().split("\n") if l.startswith("{")][-1]
                 line["e2e_cpp_host"] = json.loads(last)
