@@ -31,6 +31,7 @@ struct ilqr_handle {
   int *phHostCount = nullptr; /* pinned: active-list lengths read back while the trips run */
   cudaEvent_t phEvent[2] = {nullptr, nullptr};
   bool phReady = false;
+  bool phNoCand = false; /* the candidate buffers did not fit: the line search re-rolls the accepted candidate */
   unsigned long long *queue = nullptr;
   int num_sms = 0;
   int64_t launches = 0;

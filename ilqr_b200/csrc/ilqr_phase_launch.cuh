@@ -31,19 +31,40 @@ constexpr long long kPhaseHandover = 3200;
  * 9.2 M it/s, configs[2] 5.7 -> 3.4 M it/s (gpurun_out/r2t).  For batches whose candidate buffers would not fit. */
 constexpr long long kPhaseRerollMin = 1LL << 62;
 
+inline void phase_release(ilqr_handle *h) {
+  void **bufs[] = {&h->phF, &h->phC, &h->phCandX, &h->phCandU, &h->phNewcost, &h->phGterm, (void **)&h->phAct, (void **)&h->phNact};
+  for (void **b : bufs) {
+    if (*b) cudaFree(*b);
+    *b = nullptr;
+  }
+  h->phReady = false;
+}
+
+/* The per-trajectory buffers of the phase kernels.  Returns kPhaseNoMemory (and releases what it had taken) when the
+ * batch's stored derivatives do not fit beside its trajectories: the caller then runs the persistent kernel, whose
+ * work buffers are per resident warp, not per trajectory — same results, any batch the trajectories themselves fit. */
+constexpr int kPhaseNoMemory = 1000;
 template <class Model, typename S, int CD>
 int phase_prepare(ilqr_handle *h) {
   if (h->phReady) return ILQR_OK;
   constexpr size_t N = Model::N, M = Model::M, NM = N + M, NCF = NM + NM * NM;
   const size_t B = (size_t)h->desc.B, T = (size_t)h->desc.T;
-  CU(h, cudaMalloc(&h->phF, B * T * NM * N * sizeof(S)));
-  if (CD == kCostFD) CU(h, cudaMalloc(&h->phC, B * T * NCF * sizeof(S)));
-  CU(h, cudaMalloc(&h->phNewcost, B * kMaxAlpha * sizeof(S)));
-  CU(h, cudaMalloc(&h->phGterm, B * T * sizeof(S)));
-  CU(h, cudaMalloc((void **)&h->phAct, 2 * B * sizeof(int)));
-  CU(h, cudaMalloc((void **)&h->phNact, 2 * sizeof(int)));
-  CU(h, cudaMallocHost((void **)&h->phHostCount, 2 * sizeof(int)));
-  for (int i = 0; i < 2; i++) CU(h, cudaEventCreateWithFlags(&h->phEvent[i], cudaEventDisableTiming));
+  if (B > (size_t)1 << 30) return kPhaseNoMemory; /* the active lists index trajectories with 32-bit integers */
+  bool ok = cudaMalloc(&h->phF, B * T * NM * N * sizeof(S)) == cudaSuccess;
+  if (ok && CD == kCostFD) ok = cudaMalloc(&h->phC, B * T * NCF * sizeof(S)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->phNewcost, B * kMaxAlpha * sizeof(S)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->phGterm, B * T * sizeof(S)) == cudaSuccess;
+  ok = ok && cudaMalloc((void **)&h->phAct, 2 * B * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void **)&h->phNact, 2 * sizeof(int)) == cudaSuccess;
+  if (!ok) {
+    const cudaError_t e = cudaGetLastError(); /* also clears it */
+    phase_release(h);
+    if (e == cudaErrorMemoryAllocation) return kPhaseNoMemory;
+    return ilqr_fail(h, ILQR_E_CUDA, std::string("phase buffers: ") + cudaGetErrorString(e));
+  }
+  if (!h->phHostCount) CU(h, cudaMallocHost((void **)&h->phHostCount, 2 * sizeof(int)));
+  for (int i = 0; i < 2; i++)
+    if (!h->phEvent[i]) CU(h, cudaEventCreateWithFlags(&h->phEvent[i], cudaEventDisableTiming));
   h->phReady = true;
   return ILQR_OK;
 }
@@ -51,6 +72,12 @@ int phase_prepare(ilqr_handle *h) {
 template <class Model, typename S, int CD>
 int phase_iterate_t(ilqr_handle *h, int n_iters) {
   const int rc = phase_prepare<Model, S, CD>(h);
+  if (rc == kPhaseNoMemory || getenv("ILQR_B200_TEST_NO_PHASE_MEMORY")) { /* (the variable: the tests' way to take this branch) */
+    phase_release(h);
+    h->engine_warp = true; /* for the rest of this handle's life */
+    return h->desc.model_id == ILQR_MODEL_ACROBOT ? ILQR_ENTRY(ilqr_launch_acrobot)(h, kOpIterate, n_iters, 0.0)
+                                                  : ILQR_ENTRY(ilqr_launch_double_integrator)(h, kOpIterate, n_iters, 0.0);
+  }
   if (rc != ILQR_OK) return rc;
   PArgs<S> a;
   if (make_solve_params<S>(h->desc, &a.P) != 0) return ilqr_fail(h, ILQR_E_INVALID, "bad parameters");
@@ -138,11 +165,17 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
       phase_backward_kernel<Model, S, CD><<<(unsigned)((bound + kBackwardThreads - 1) / kBackwardThreads), kBackwardThreads, 0, st>>>(a);
       h->launches += 2;
     }
-    a.reroll = bound > reroll_min;
+    a.reroll = bound > reroll_min || h->phNoCand;
     if (!a.reroll && !h->phCandX) { /* the candidate buffers, on first use */
       const size_t B = (size_t)h->desc.B, T = (size_t)h->desc.T;
-      CU(h, cudaMalloc(&h->phCandX, B * T * na * N * sizeof(S)));
-      CU(h, cudaMalloc(&h->phCandU, B * T * na * M * sizeof(S)));
+      const bool ok = !getenv("ILQR_B200_TEST_NO_CAND_MEMORY") && cudaMalloc(&h->phCandX, B * T * na * N * sizeof(S)) == cudaSuccess &&
+                      cudaMalloc(&h->phCandU, B * T * na * M * sizeof(S)) == cudaSuccess;
+      if (!ok) { /* they do not fit: cost-only rollouts and one re-roll of the accepted candidate instead — same results */
+        (void)cudaGetLastError();
+        if (h->phCandX) cudaFree(h->phCandX);
+        h->phCandX = h->phCandU = nullptr;
+        h->phNoCand = a.reroll = true;
+      }
       a.buf.cand_x = (S *)h->phCandX;
       a.buf.cand_u = (S *)h->phCandU;
     }

@@ -333,6 +333,36 @@ def test_phase_engine_reroll_mode(model, cd, dtype, T, kw, head, monkeypatch):
             assert np.array_equal(s.get(f), ref.get(f)), (reroll_min, f)
 
 
+@pytest.mark.parametrize("which", ["ILQR_B200_TEST_NO_CAND_MEMORY", "ILQR_B200_TEST_NO_PHASE_MEMORY"])
+@pytest.mark.parametrize("cd", [abi.COST_ANALYTIC, abi.COST_FD])
+def test_phase_engine_when_its_buffers_do_not_fit(which, cd, monkeypatch):
+    """a batch whose per-trajectory work buffers do not fit in HBM beside its trajectories (ilqr_phase_launch.cuh):
+    without the candidate buffers the line search re-rolls the accepted candidate; without the stored derivatives
+    the persistent kernel runs the solve.  Neither is an error and both return the same bits.  (The variables
+    make the allocations "fail" at a size the test can afford.)"""
+    B, T = 150, 120
+    x0, u0 = make_inputs(4242, B, T, 4, 1)
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")
+    ref = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cd)
+    ref.generate_trajectory(x0, u0)
+    monkeypatch.setenv(which, "1")
+    s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=cd)
+    s.generate_trajectory(x0, u0)
+    for f in ALL_FIELDS:
+        assert np.array_equal(s.get(f), ref.get(f)), f
+    if which.endswith("PHASE_MEMORY"):
+        assert s.launch_count < ref.launch_count          # one persistent launch instead of lockstep rounds
+    else:
+        assert s.launch_count > ref.launch_count          # the extra commit kernel of the re-roll mode
+    s.warm_start(x0 + 0.01)
+    ref.warm_start(x0 + 0.01)
+    monkeypatch.delenv(which)                              # the decision, once taken, holds for the handle
+    s.generate_trajectory()
+    ref.generate_trajectory()
+    for f in ALL_FIELDS:
+        assert np.array_equal(s.get(f), ref.get(f)), f
+
+
 @pytest.mark.parametrize("handover,check", [(150, 1), (250, 3), (40, 8)])
 def test_phase_engine_hands_the_tail_to_the_persistent_kernel(handover, check, monkeypatch):
     """lockstep rounds while many trajectories run, then the persistent warp kernel for the survivors' remaining trips
