@@ -23,6 +23,23 @@ constexpr int kPhaseCheckEvery = 8; /* trips between read-backs of the active co
  * (2368 resident warps).  Measured on BASELINE configs[1] (gpurun_out r2h/r2i): 59.7 ms lockstep only, 48.8 ms with
  * the hand-over at 3200, 53.3 ms persistent kernel only. */
 constexpr long long kPhaseHandover = 3200;
+/* Running trajectories above which the line search is staged (ilqr_phases.cuh: PArgs::stage), and the size of the
+ * first stage.  62 % of the line searches of the synthetic batch accept one of the first four candidates (23 / 16 /
+ * 14 / 9 %; 28 % reject all eleven), so staging rolls out 40 % fewer candidates and writes a third of the candidate
+ * bytes (configs[4] shard: 870 GB of DRAM traffic per solve instead of 1203).  OFF by default (environment
+ * ILQR_B200_STAGE_MIN turns it on): it was slower at every size measured — configs[4] shard 11.1 -> 9.5 M it/s (k = 4),
+ * 10.1 (k = 6); configs[2] 5.7 -> 3.8; configs[1] 3.50 -> 3.11 (gpurun_out/st3, profiles/experiments/README.md).  A
+ * rollout launch costs its 200-step chain however few candidates it carries, so two stages pay it twice; the re-roll
+ * of the steps accepted in stage 2 is one thread per trajectory at DRAM latency per timestep (65 ms per solve for 0.6 %
+ * of the instructions); and the backward phase lost 16 % on an active list that is no longer in ascending order. */
+constexpr long long kPhaseStageMin = 1LL << 62;
+constexpr int kPhaseStageK = 4;
+/* Running trajectories above which the next active list is built by order-preserving compaction (ilqr_phases.cuh:
+ * phase_compact_kernel; one more launch per trip) instead of atomic append.  The 32 trajectories of a warp of the
+ * thread-per-trajectory kernels are then neighbours in memory (1 MB of Jacobians instead of a sample of ~80 MB:
+ * TLB reach and open DRAM pages): configs[4] shard 11.0 -> 12.4 M it/s, configs[2] 5.74 -> 5.96, configs[3] +0.6 %;
+ * at 4096 trajectories the extra launch costs what the order gains (gpurun_out/ord1). */
+constexpr long long kPhaseOrderedMin = 8192;
 /* Running trajectories above which the line search stores no candidates (cost-only rollouts + one re-roll of the
  * accepted candidate, ilqr_phases.cuh: rollout_task).  OFF by default (environment ILQR_B200_REROLL_MIN turns it on):
  * it removes the candidate buffers (88 KB per trajectory at T = 200) and 40 % of the DRAM traffic of configs[4]
@@ -54,8 +71,8 @@ int phase_prepare(ilqr_handle *h) {
   if (ok && CD == kCostFD) ok = cudaMalloc(&h->phC, B * T * NCF * sizeof(S)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->phNewcost, B * kMaxAlpha * sizeof(S)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->phGterm, B * T * sizeof(S)) == cudaSuccess;
-  ok = ok && cudaMalloc((void **)&h->phAct, 2 * B * sizeof(int)) == cudaSuccess;
-  ok = ok && cudaMalloc((void **)&h->phNact, 2 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void **)&h->phAct, 5 * B * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void **)&h->phNact, 4 * sizeof(int)) == cudaSuccess;
   if (!ok) {
     const cudaError_t e = cudaGetLastError(); /* also clears it */
     phase_release(h);
@@ -102,7 +119,7 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
   a.reroll = 0;
   a.force_sweep = 1;
   cudaStream_t st = h->stream;
-  CU(h, cudaMemsetAsync(h->phNact, 0, 2 * sizeof(int), st));
+  CU(h, cudaMemsetAsync(h->phNact, 0, 4 * sizeof(int), st));
   {
     const unsigned blocks = (unsigned)((a.B + 255) / 256);
     phase_begin_kernel<S><<<blocks, 256, 0, st>>>(a);
@@ -125,6 +142,14 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
    * (ilqr_phases.cuh: rollout_task) */
   long long reroll_min = kPhaseRerollMin;
   if (const char *e = getenv("ILQR_B200_REROLL_MIN")) reroll_min = atoll(e);
+  /* above this many running trajectories the line search is staged: first stage_k candidates, then the rest */
+  long long stage_min = kPhaseStageMin;
+  if (const char *e = getenv("ILQR_B200_STAGE_MIN")) stage_min = atoll(e);
+  /* above this many running trajectories the next active list keeps the order of this one (phase_compact_kernel) */
+  long long ordered_min = kPhaseOrderedMin;
+  if (const char *e = getenv("ILQR_B200_ORDERED_MIN")) ordered_min = atoll(e);
+  int stage_k = kPhaseStageK;
+  if (const char *e = getenv("ILQR_B200_STAGE_K")) stage_k = atoi(e);
   if (const char *e = getenv("ILQR_B200_CHECK_EVERY")) check_every = atoi(e) > 0 ? atoi(e) : check_every;
   constexpr int N = Model::N, M = Model::M;
   const size_t pre_smem = warp_smem_bytes<typename Core<Model, S, CD, WarpExec<N, M, S, 32>>::Sc, S>(h->desc.T) * kWarpsPerCta;
@@ -179,15 +204,30 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
       a.buf.cand_x = (S *)h->phCandX;
       a.buf.cand_u = (S *)h->phCandU;
     }
-    if (a.reroll)
-      phase_rollout_kernel<Model, S, CD, Phases<Model, S, CD>::kCostOnly>
-          <<<(unsigned)((bound * na + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
-    else
-      phase_rollout_kernel<Model, S, CD, Phases<Model, S, CD>::kToCand>
-          <<<(unsigned)((bound * na + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
-    phase_accept_kernel<Model, S, CD><<<(unsigned)((bound * 32 + kAcceptThreads - 1) / kAcceptThreads), kAcceptThreads, 0, st>>>(a);
-    h->launches += 2;
-    if (a.reroll) {
+    /* the line search: all candidates at once, or — large active sets — the first stage_k, then the rest (cost only)
+     * for the trajectories where none of those passed (ilqr_phases.cuh: PArgs::stage) */
+    const bool staged = bound > stage_min && stage_k > 0 && stage_k < na;
+    a.ordered = !staged && bound > ordered_min;
+    for (int stage = staged ? 1 : 0; stage <= (staged ? 2 : 0); stage++) {
+      a.stage = stage;
+      a.cand_lo = stage == 2 ? stage_k : 0;
+      a.cand_hi = stage == 1 ? stage_k : na;
+      a.keep = !a.reroll && stage != 2;
+      const long long nthr = bound * (a.cand_hi - a.cand_lo); /* stage 2: an upper bound, its list is on the device */
+      if (a.keep)
+        phase_rollout_kernel<Model, S, CD, Phases<Model, S, CD>::kToCand>
+            <<<(unsigned)((nthr + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
+      else
+        phase_rollout_kernel<Model, S, CD, Phases<Model, S, CD>::kCostOnly>
+            <<<(unsigned)((nthr + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
+      phase_accept_kernel<Model, S, CD><<<(unsigned)((bound * 32 + kAcceptThreads - 1) / kAcceptThreads), kAcceptThreads, 0, st>>>(a);
+      h->launches += 2;
+    }
+    if (a.ordered) {
+      phase_compact_kernel<S><<<1, kCompactThreads, 0, st>>>(a);
+      h->launches += 1;
+    }
+    if (a.reroll || staged) { /* the accepted steps whose rollouts were not kept (list 3; the grid is an upper bound) */
       phase_commit_kernel<Model, S, CD><<<(unsigned)((bound + kRolloutThreads - 1) / kRolloutThreads), kRolloutThreads, 0, st>>>(a);
       h->launches += 1;
     }

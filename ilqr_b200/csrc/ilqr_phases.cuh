@@ -143,8 +143,10 @@ struct PhaseBufs {
   S *cand_u;  /* [B][T][n_alpha][m]  candidate controls */
   S *newcost; /* [B][kMaxAlpha]      */
   S *gterm;   /* [B][T]              per-timestep terms of the gradient norm, written by the backward phase */
-  int *act;   /* [2][B]              active lists, double-buffered by trip parity */
-  int *n_act; /* [2]                 their lengths */
+  int *act;   /* [5][B]              active lists: two double-buffered by trip parity; [2] = stage 2 of a staged line
+                                     search; [3] = accepted steps to re-roll (phase_commit_kernel); [4] = per list
+                                     position, "runs another trip" (phase_compact_kernel) */
+  int *n_act; /* [4]                 their lengths */
 };
 
 template <class Model, typename S, int CD>
@@ -529,8 +531,9 @@ struct Phases {
    * accepted candidate (one extra rollout in eleven; same operations, same bits). */
   enum { kToCand = 0, kCostOnly = 1, kInPlace = 2 };
   template <int MODE>
-  ILQR_HD static S rollout_task(const SolveParams<S> &P, const TrajPtrs<S> &tr, S *cand_x, S *cand_u, int a) {
+  ILQR_HD static S rollout_task(const SolveParams<S> &P, const TrajPtrs<S> &tr, S *cand_x, S *cand_u, int a, int cand_w = -1) {
     const int T = P.T;
+    if (cand_w < 0) cand_w = P.n_alpha; /* candidates kept per timestep (the first stage of a staged line search keeps fewer) */
     const S alpha = P.alpha[a];
     const S *mp = P.mp;
     S x[N], cost = 0;
@@ -573,8 +576,8 @@ struct Phases {
 #pragma unroll
       for (int i = 0; i < N; i++) x[i] = x1[i];
       if constexpr (MODE == kToCand) {
-        store_run<M>(cand_u + ((size_t)t * P.n_alpha + a) * M, uc);
-        store_run<N>(cand_x + ((size_t)t * P.n_alpha + a) * N, x);
+        store_run<M>(cand_u + ((size_t)t * cand_w + a) * M, uc);
+        store_run<N>(cand_x + ((size_t)t * cand_w + a) * N, x);
       } else if constexpr (MODE == kInPlace) {
         store_run<M>(tr.us + (size_t)t * M, uc);
         store_run<N>(tr.xs + (size_t)(t + 1) * N, x);
@@ -588,13 +591,14 @@ struct Phases {
 
   /* the acceptance test (:199-213) in the reference's serial order over the candidates' costs; true = a step was
    * accepted (s.alpha_index says which) */
-  ILQR_HD static bool accept(const SolveParams<S> &P, TrajState<S> &s, const S *newcost) {
+  ILQR_HD static bool accept(const SolveParams<S> &P, TrajState<S> &s, const S *newcost, int n_try = -1) {
     const bool back_done = s.roll == kRollGo;
+    if (n_try < 0) n_try = P.n_alpha; /* a staged line search (phase_accept_kernel) looks at the first few only */
     bool fwd_done = false;
     s.alpha_index = -1;
     S alpha = 0;
     if (back_done) {
-      for (int a = 0; a < P.n_alpha; a++) {
+      for (int a = 0; a < n_try; a++) {
         alpha = P.alpha[a];
         s.new_cost = newcost[a];
         s.n_rollouts++;
@@ -658,6 +662,16 @@ struct PArgs {
   int parity;      /* which active list this trip reads */
   int force_sweep; /* first trip of an ilqr_iterate call: F / C may be stale (set_initial, warm start, test hooks) */
   int reroll;      /* this trip's line search keeps no candidates: the accepted one is re-rolled (phase_commit_kernel) */
+  /* Staged line search (large active sets): stage 1 rolls out candidates [0, cand_hi) of every trajectory, keeps them
+   * ([T][cand_hi][.]: with four, a timestep's states are one 128-byte line) and accepts where one of them passes;
+   * the trajectories where none does go to list 2, and stage 2 rolls out [cand_lo, n_alpha) for them, cost only.  A
+   * step accepted there (one line search in ten) goes to list 3 and is re-rolled over xs / us (phase_commit_kernel).
+   * The reference tries the candidates in order and stops at the first that passes (:186-214), so the candidates
+   * after it were never needed: 62 % of the line searches of the synthetic batch end within four, 28 % reject all.
+   * stage 0 = all candidates at once (small active sets: latency, not work, is what a round costs). */
+  int stage, cand_lo, cand_hi;
+  int ordered; /* the next active list is built in the order of this one (phase_compact_kernel), not by atomic append */
+  int keep; /* this stage's rollouts were stored (cand_hi per timestep): an accepted one is copied, otherwise re-rolled */
 };
 
 template <typename S>
@@ -732,7 +746,7 @@ __global__ void __launch_bounds__(kBackwardThreads, ILQR_BACKWARD_MINB) phase_ba
   constexpr int N = Model::N, M = Model::M, NM = N + M;
   const int n_act = a.buf.n_act[a.parity];
   const int i = blockIdx.x * kBackwardThreads + threadIdx.x;
-  if (i == 0) a.buf.n_act[a.parity ^ 1] = 0; /* the list this trip's accept phase fills */
+  if (i == 0) a.buf.n_act[a.parity ^ 1] = a.buf.n_act[2] = a.buf.n_act[3] = 0; /* the lists this trip's accept phase fills */
   const unsigned mask = __ballot_sync(0xffffffffu, i < n_act);
   if (i >= n_act) return;
   const long long b = a.buf.act[(size_t)a.parity * a.B + i];
@@ -794,7 +808,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) phase_backward_rows_kernel(con
   const int grp = (threadIdx.x >> 5) * GPW + wl / G, lane = wl % G;
   const int n_act = a.buf.n_act[a.parity];
   const int i = (wl / G < GPW) ? blockIdx.x * kPerCta + grp : 0x7fffffff;
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.buf.n_act[a.parity ^ 1] = 0; /* the list this trip's accept phase fills */
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.buf.n_act[a.parity ^ 1] = a.buf.n_act[2] = a.buf.n_act[3] = 0; /* the lists this trip's accept phase fills */
   /* The four trajectories of a warp advance in lockstep: every barrier below is warp-wide (over the lanes that carry a
    * trajectory), so the row products and the value update of the four groups issue as ONE instruction stream with
    * 4 x (n + m) lanes active, and only the boxQP lanes ever run apart.  (With group-wide barriers the groups drifted
@@ -1168,7 +1182,7 @@ __global__ void __launch_bounds__(kThreads, ILQR_MIN_BLOCKS) phase_pre_warp_kern
   Sc &sc = *reinterpret_cast<Sc *>(mine);
   const int n_act = a.buf.n_act[a.parity];
   const int i = blockIdx.x * kWarpsPerCta + group;
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.buf.n_act[a.parity ^ 1] = 0; /* the list this trip's accept phase fills */
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.buf.n_act[a.parity ^ 1] = a.buf.n_act[2] = a.buf.n_act[3] = 0; /* the lists this trip's accept phase fills */
   if (i >= n_act) return;
   const long long b = a.buf.act[(size_t)a.parity * a.B + i];
   const size_t T = (size_t)a.P.T;
@@ -1204,37 +1218,36 @@ template <class Model, typename S, int CD, int MODE>
 __global__ void __launch_bounds__(kRolloutThreads, ILQR_ROLLOUT_MINB) phase_rollout_kernel(const __grid_constant__ PArgs<S> a) {
   using Ph = Phases<Model, S, CD>;
   constexpr int N = Model::N, M = Model::M;
-  const int n_act = a.buf.n_act[a.parity];
-  const int na = a.P.n_alpha;
+  const int list = a.stage == 2 ? 2 : a.parity;
+  const int n_act = a.buf.n_act[list];
+  const int na = a.P.n_alpha, nc = a.cand_hi - a.cand_lo;
   const long long tid = blockIdx.x * (long long)kRolloutThreads + threadIdx.x;
-  const long long i = tid / na;
+  const long long i = tid / nc;
   if (i >= n_act) return;
-  const int cand = (int)(tid - i * na);
-  const long long b = a.buf.act[(size_t)a.parity * a.B + i];
+  const int cand = a.cand_lo + (int)(tid - i * nc);
+  const long long b = a.buf.act[(size_t)list * a.B + i];
   if (a.st[b].roll != kRollGo) return;
   const TrajPtrs<S> tr = phase_pointers(a, b, N, M);
   const size_t T = (size_t)a.P.T;
   /* MODE is a template parameter: with both variants behind a run-time branch the kernel carried two copies of the hot
    * loop and configs[4] lost 20 % */
   const S c = Ph::template rollout_task<MODE>(a.P, tr, MODE == Ph::kToCand ? a.buf.cand_x + b * T * na * N : nullptr,
-                                              MODE == Ph::kToCand ? a.buf.cand_u + b * T * na * M : nullptr, cand);
+                                              MODE == Ph::kToCand ? a.buf.cand_u + b * T * na * M : nullptr, cand, a.cand_hi);
   a.buf.newcost[b * kMaxAlpha + cand] = c;
 }
 
-/* re-roll mode: the accepted candidate of every trajectory that took a step this trip, rolled out once more over
- * xs / us (one thread per trajectory; runs after the accept phase, which has recorded alpha_index) */
+/* the steps accepted from rollouts that were not kept (re-roll mode; stage 2 of a staged line search), rolled out once
+ * more over xs / us: one thread per trajectory of list 3, which the accept phase has filled */
 template <class Model, typename S, int CD>
 __global__ void __launch_bounds__(kRolloutThreads, ILQR_ROLLOUT_MINB) phase_commit_kernel(const __grid_constant__ PArgs<S> a) {
   using Ph = Phases<Model, S, CD>;
   constexpr int N = Model::N, M = Model::M;
-  const int n_act = a.buf.n_act[a.parity];
+  const int n_act = a.buf.n_act[3];
   const long long i = blockIdx.x * (long long)kRolloutThreads + threadIdx.x;
   if (i >= n_act) return;
-  const long long b = a.buf.act[(size_t)a.parity * a.B + i];
-  const TrajState<S> &s = a.st[b];
-  if (s.roll != kRollGo || s.alpha_index < 0) return; /* no line search this trip, or no step taken */
+  const long long b = a.buf.act[(size_t)3 * a.B + i];
   const TrajPtrs<S> tr = phase_pointers(a, b, N, M);
-  Ph::template rollout_task<Ph::kInPlace>(a.P, tr, nullptr, nullptr, s.alpha_index);
+  Ph::template rollout_task<Ph::kInPlace>(a.P, tr, nullptr, nullptr, a.st[b].alpha_index);
 }
 
 constexpr int kAcceptThreads = 128;
@@ -1242,26 +1255,36 @@ template <class Model, typename S, int CD>
 __global__ void __launch_bounds__(kAcceptThreads) phase_accept_kernel(const __grid_constant__ PArgs<S> a) {
   using Ph = Phases<Model, S, CD>;
   constexpr int N = Model::N, M = Model::M;
-  const int n_act = a.buf.n_act[a.parity];
+  const int list = a.stage == 2 ? 2 : a.parity;
+  const int n_act = a.buf.n_act[list];
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * kAcceptThreads) >> 5;
   const int na = a.P.n_alpha;
   const size_t T = (size_t)a.P.T;
   for (int i = (blockIdx.x * kAcceptThreads + threadIdx.x) >> 5; i < n_act; i += warps) {
-    const long long b = a.buf.act[(size_t)a.parity * a.B + i];
+    const long long b = a.buf.act[(size_t)list * a.B + i];
     TrajState<S> *st = a.st + b;
     int code = 0; /* bit 0: accepted; bits 8..: alpha index */
+    if (lane == 0 && a.ordered) a.buf.act[(size_t)4 * a.B + i] = 0;
     if (lane == 0 && st->status == kRunning) {
       TrajState<S> s = *st;
-      const bool fwd = Ph::accept(a.P, s, a.buf.newcost + b * kMaxAlpha);
-      code = fwd ? (1 | (s.alpha_index << 8)) : 0;
-      const bool go_on = Ph::schedule(a.P, s, fwd);
-      *st = s;
-      if (go_on) a.buf.act[(size_t)(a.parity ^ 1) * a.B + atomicAdd(&a.buf.n_act[a.parity ^ 1], 1)] = (int)b;
+      const bool fwd = Ph::accept(a.P, s, a.buf.newcost + b * kMaxAlpha, a.stage == 1 ? a.cand_hi : na);
+      if (a.stage == 1 && !fwd && s.roll == kRollGo) {
+        /* none of the first few passed: stage 2 decides, from the state as it was (nothing is written back here) */
+        a.buf.act[(size_t)2 * a.B + atomicAdd(&a.buf.n_act[2], 1)] = (int)b;
+      } else {
+        code = fwd ? (1 | (s.alpha_index << 8)) : 0;
+        const bool go_on = Ph::schedule(a.P, s, fwd);
+        *st = s;
+        if (go_on && a.ordered) a.buf.act[(size_t)4 * a.B + i] = 1;
+        else if (go_on) a.buf.act[(size_t)(a.parity ^ 1) * a.B + atomicAdd(&a.buf.n_act[a.parity ^ 1], 1)] = (int)b;
+      }
     }
     code = __shfl_sync(0xffffffffu, code, 0);
-    if ((code & 1) && !a.reroll) { /* xs[1..T], us[0..T-1] <- the accepted candidate (what forward_pass left, :323,334) */
-      const int ai = code >> 8;
+    if ((code & 1) && !a.keep) { /* not kept: phase_commit_kernel re-rolls it */
+      if (lane == 0) a.buf.act[(size_t)3 * a.B + atomicAdd(&a.buf.n_act[3], 1)] = (int)b;
+    } else if (code & 1) { /* xs[1..T], us[0..T-1] <- the accepted candidate (what forward_pass left, :323,334) */
+      const int ai = code >> 8, cw = a.cand_hi;
       const S *cx = a.buf.cand_x + b * T * na * N;
       const S *cu = a.buf.cand_u + b * T * na * M;
       S *xs = a.xs + b * (T + 1) * N + N;
@@ -1269,14 +1292,49 @@ __global__ void __launch_bounds__(kAcceptThreads) phase_accept_kernel(const __gr
       const int nx = (int)T * N, nu = (int)T * M;
       for (int e = lane; e < nx; e += 32) {
         const int t = e / N, c = e - t * N;
-        xs[e] = cx[((size_t)t * na + ai) * N + c];
+        xs[e] = cx[((size_t)t * cw + ai) * N + c];
       }
       for (int e = lane; e < nu; e += 32) {
         const int t = e / M, c = e - t * M;
-        us[e] = cu[((size_t)t * na + ai) * M + c];
+        us[e] = cu[((size_t)t * cw + ai) * M + c];
       }
     }
   }
+}
+
+/* The next trip's active list in the ORDER of this one (the first is 0 .. B-1, so every list stays ascending): one
+ * CTA walks the flags the accept phase left and appends the survivors.  The 32 trajectories of a warp of the
+ * thread-per-trajectory kernels are then neighbours in memory, not a sample of whatever the atomics of ~2000
+ * concurrent warps interleaved. */
+constexpr int kCompactThreads = 1024;
+template <typename S>
+__global__ void __launch_bounds__(kCompactThreads) phase_compact_kernel(const __grid_constant__ PArgs<S> a) {
+  __shared__ int warp_total[kCompactThreads / 32];
+  __shared__ int base;
+  const int n = a.buf.n_act[a.parity];
+  const int *src = a.buf.act + (size_t)a.parity * a.B, *flag = a.buf.act + (size_t)4 * a.B;
+  int *dst = a.buf.act + (size_t)(a.parity ^ 1) * a.B;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += kCompactThreads) {
+    const int i = start + threadIdx.x;
+    const bool f = i < n && flag[i] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_total[w] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int q = 0; q < w; q++) off += warp_total[q];
+    if (f) dst[off + __popc(bal & ((1u << lane) - 1))] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int q = 0; q < kCompactThreads / 32; q++) tot += warp_total[q];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.buf.n_act[a.parity ^ 1] = base;
 }
 
 #endif /* __CUDACC__ */

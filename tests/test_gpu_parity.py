@@ -333,6 +333,62 @@ def test_phase_engine_reroll_mode(model, cd, dtype, T, kw, head, monkeypatch):
             assert np.array_equal(s.get(f), ref.get(f)), (reroll_min, f)
 
 
+@pytest.mark.parametrize("model,cd,dtype,T,kw", [
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F64, 200, {}),
+    (abi.MODEL_ACROBOT, abi.COST_FD, abi.F64, 120, dict(u_min=[-1.5], u_max=[1.5])),
+    (abi.MODEL_ACROBOT, abi.COST_ANALYTIC, abi.F32, 300, {}),
+    (abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, abi.F64, 60, dict(goal=[1.0, 1.0, 0.0, 0.0])),
+])
+@pytest.mark.parametrize("stage_k,reroll", [(4, False), (1, False), (10, False), (3, True)])
+def test_phase_engine_staged_line_search(model, cd, dtype, T, kw, stage_k, reroll, monkeypatch):
+    """the line search of large active sets in two stages (ilqr_phases.cuh: PArgs::stage): the first stage_k candidates
+    of every trajectory, then the remaining ones only where none of those passed.  The reference tries the candidates
+    in order and stops at the first that passes (src/ilqr_core.cpp:186-214), so nothing it would have looked at is
+    skipped: same bits as all-at-once and as the warp engine, counters (n_rollouts, alpha_index) included; also when
+    the staging switches off in mid-solve and in the re-roll mode."""
+    B = 200
+    n, m = abi.MODEL_DIMS[model]
+    x0, u0 = make_inputs(909, B, T, n, m)
+    dt = 0.02 if model == abi.MODEL_ACROBOT else 0.05
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")
+    ref = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, flags=abi.FLAG_ENGINE_WARP, **kw)
+    ref.generate_trajectory(x0, u0)
+    monkeypatch.setenv("ILQR_B200_STAGE_K", str(stage_k))
+    if reroll:
+        monkeypatch.setenv("ILQR_B200_REROLL_MIN", "0")
+    launches = []
+    for stage_min, check in (("0", "8"), ("100", "1")):       # staged to the end; staged until 100 are left
+        monkeypatch.setenv("ILQR_B200_STAGE_MIN", stage_min)
+        monkeypatch.setenv("ILQR_B200_CHECK_EVERY", check)
+        s = BatchILQR(model, T=T, B=B, dt=dt, cost_deriv=cd, dtype=dtype, **kw)
+        s.generate_trajectory(x0, u0)
+        for f in ALL_FIELDS:
+            assert np.array_equal(s.get(f), ref.get(f)), (stage_min, f)
+        launches.append(s.launch_count)
+    assert launches[0] > launches[1]                          # two more launches per staged trip
+
+
+@pytest.mark.parametrize("head", ["rows", "thread"])
+@pytest.mark.parametrize("B", [77, 1500, 2100])
+def test_phase_engine_ordered_active_list(B, head, monkeypatch):
+    """the next trip's active list by order-preserving compaction (phase_compact_kernel) instead of atomic append: the
+    same set of trajectories in ascending order, so the same bits; batch sizes below, across and above one pass of
+    the compacting CTA (1024 entries)"""
+    T = 60
+    x0, u0 = make_inputs(31337, B, T, 4, 1)
+    monkeypatch.setenv("ILQR_B200_HANDOVER", "0")
+    monkeypatch.setenv("ILQR_B200_ROWS_MAX", "0" if head == "thread" else "1000000")
+    ref = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC, flags=abi.FLAG_ENGINE_WARP)
+    ref.generate_trajectory(x0, u0)
+    for ordered_min in ("0", str(B // 2)):
+        monkeypatch.setenv("ILQR_B200_ORDERED_MIN", ordered_min)
+        monkeypatch.setenv("ILQR_B200_CHECK_EVERY", "1")
+        s = BatchILQR(abi.MODEL_ACROBOT, T=T, B=B, dt=0.02, cost_deriv=abi.COST_ANALYTIC)
+        s.generate_trajectory(x0, u0)
+        for f in ALL_FIELDS:
+            assert np.array_equal(s.get(f), ref.get(f)), (ordered_min, f)
+
+
 @pytest.mark.parametrize("which", ["ILQR_B200_TEST_NO_CAND_MEMORY", "ILQR_B200_TEST_NO_PHASE_MEMORY"])
 @pytest.mark.parametrize("cd", [abi.COST_ANALYTIC, abi.COST_FD])
 def test_phase_engine_when_its_buffers_do_not_fit(which, cd, monkeypatch):
