@@ -35,11 +35,12 @@ constexpr long long kPhaseHandover = 3200;
 constexpr long long kPhaseStageMin = 1LL << 62;
 constexpr int kPhaseStageK = 4;
 /* Running trajectories above which the next active list is built by order-preserving compaction (ilqr_phases.cuh:
- * phase_compact_kernel; one more launch per trip) instead of atomic append.  The 32 trajectories of a warp of the
- * thread-per-trajectory kernels are then neighbours in memory (1 MB of Jacobians instead of a sample of ~80 MB:
- * TLB reach and open DRAM pages): configs[4] shard 11.0 -> 12.4 M it/s, configs[2] 5.74 -> 5.96, configs[3] +0.6 %;
- * at 4096 trajectories the extra launch costs what the order gains (gpurun_out/ord1). */
-constexpr long long kPhaseOrderedMin = 8192;
+ * phase_compact_kernel; one more launch per trip, ~10 us) instead of atomic append.  The 32 trajectories of a warp of
+ * the thread-per-trajectory kernels are then neighbours in memory (1 MB of Jacobians instead of a sample of ~80 MB:
+ * TLB reach and open DRAM pages; ncu long-scoreboard stalls of the backward phase 0.73 -> 0.26 per issue at trip 2 and
+ * its time over a solve 173 -> 113 ms): configs[4] shard 11.0 -> 12.4 M it/s, configs[2] 5.74 -> 5.96, configs[3]
+ * +1 %, configs[1] +0.5 % (gpurun_out/ord1, acc1). */
+constexpr long long kPhaseOrderedMin = 2048;
 /* Running trajectories above which the line search stores no candidates (cost-only rollouts + one re-roll of the
  * accepted candidate, ilqr_phases.cuh: rollout_task).  OFF by default (environment ILQR_B200_REROLL_MIN turns it on):
  * it removes the candidate buffers (88 KB per trajectory at T = 200) and 40 % of the DRAM traffic of configs[4]

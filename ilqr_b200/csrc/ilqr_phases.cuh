@@ -1285,18 +1285,32 @@ __global__ void __launch_bounds__(kAcceptThreads) phase_accept_kernel(const __gr
       if (lane == 0) a.buf.act[(size_t)3 * a.B + atomicAdd(&a.buf.n_act[3], 1)] = (int)b;
     } else if (code & 1) { /* xs[1..T], us[0..T-1] <- the accepted candidate (what forward_pass left, :323,334) */
       const int ai = code >> 8, cw = a.cand_hi;
-      const S *cx = a.buf.cand_x + b * T * na * N;
-      const S *cu = a.buf.cand_u + b * T * na * M;
-      S *xs = a.xs + b * (T + 1) * N + N;
-      S *us = a.us + b * T * M;
-      const int nx = (int)T * N, nu = (int)T * M;
-      for (int e = lane; e < nx; e += 32) {
-        const int t = e / N, c = e - t * N;
-        xs[e] = cx[((size_t)t * cw + ai) * N + c];
-      }
-      for (int e = lane; e < nu; e += 32) {
-        const int t = e / M, c = e - t * M;
-        us[e] = cu[((size_t)t * cw + ai) * M + c];
+      const S *__restrict__ cx = a.buf.cand_x + b * T * na * N + (size_t)ai * N;
+      const S *__restrict__ cu = a.buf.cand_u + b * T * na * M + (size_t)ai * M;
+      S *__restrict__ xs = a.xs + b * (T + 1) * N + N;
+      S *__restrict__ us = a.us + b * T * M;
+      /* a lane moves whole timesteps (one 128-bit run or two per state), kCopyAhead of them in flight: the candidate's
+       * states are one sector every n_alpha, so the copy is a chain of DRAM round trips unless the loads overlap
+       * (one element per lane and iteration: 25 dependent-looking iterations, ncu long scoreboard 96 per issue) */
+      constexpr int kCopyAhead = 4;
+      for (int t0 = lane; t0 < (int)T; t0 += 32 * kCopyAhead) {
+        S vx[kCopyAhead][N], vu[kCopyAhead][M];
+#pragma unroll
+        for (int j = 0; j < kCopyAhead; j++) {
+          const int t = t0 + 32 * j;
+          if (t < (int)T) {
+            load_run<N>(vx[j], cx + (size_t)t * cw * N);
+            load_run<M>(vu[j], cu + (size_t)t * cw * M);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kCopyAhead; j++) {
+          const int t = t0 + 32 * j;
+          if (t < (int)T) {
+            store_run<N>(xs + (size_t)t * N, vx[j]);
+            store_run<M>(us + (size_t)t * M, vu[j]);
+          }
+        }
       }
     }
   }
@@ -1306,26 +1320,41 @@ __global__ void __launch_bounds__(kAcceptThreads) phase_accept_kernel(const __gr
  * CTA walks the flags the accept phase left and appends the survivors.  The 32 trajectories of a warp of the
  * thread-per-trajectory kernels are then neighbours in memory, not a sample of whatever the atomics of ~2000
  * concurrent warps interleaved. */
-constexpr int kCompactThreads = 1024;
+constexpr int kCompactThreads = 1024, kCompactPer = 8;
 template <typename S>
 __global__ void __launch_bounds__(kCompactThreads) phase_compact_kernel(const __grid_constant__ PArgs<S> a) {
   __shared__ int warp_total[kCompactThreads / 32];
   __shared__ int base;
   const int n = a.buf.n_act[a.parity];
-  const int *src = a.buf.act + (size_t)a.parity * a.B, *flag = a.buf.act + (size_t)4 * a.B;
-  int *dst = a.buf.act + (size_t)(a.parity ^ 1) * a.B;
+  const int *__restrict__ src = a.buf.act + (size_t)a.parity * a.B;
+  const int *__restrict__ flag = a.buf.act + (size_t)4 * a.B;
+  int *__restrict__ dst = a.buf.act + (size_t)(a.parity ^ 1) * a.B;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
-  for (int start = 0; start < n; start += kCompactThreads) {
-    const int i = start + threadIdx.x;
-    const bool f = i < n && flag[i] != 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) warp_total[w] = __popc(bal);
+  for (int start = 0; start < n; start += kCompactThreads * kCompactPer) { /* a thread: kCompactPer consecutive entries */
+    const int i0 = start + threadIdx.x * kCompactPer;
+    int f[kCompactPer], v[kCompactPer], cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kCompactPer; j++) {
+      const bool in = i0 + j < n;
+      f[j] = in ? flag[i0 + j] : 0;
+      v[j] = in ? src[i0 + j] : 0;
+      cnt += f[j] != 0;
+    }
+    int incl = cnt; /* inclusive prefix over the warp, then over the warps */
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_total[w] = incl;
     __syncthreads();
-    int off = base;
+    int off = base + incl - cnt;
     for (int q = 0; q < w; q++) off += warp_total[q];
-    if (f) dst[off + __popc(bal & ((1u << lane) - 1))] = src[i];
+#pragma unroll
+    for (int j = 0; j < kCompactPer; j++)
+      if (f[j] != 0) dst[off++] = v[j];
     __syncthreads();
     if (threadIdx.x == 0) {
       int tot = 0;

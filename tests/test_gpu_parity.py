@@ -369,11 +369,11 @@ def test_phase_engine_staged_line_search(model, cd, dtype, T, kw, stage_k, rerol
 
 
 @pytest.mark.parametrize("head", ["rows", "thread"])
-@pytest.mark.parametrize("B", [77, 1500, 2100])
+@pytest.mark.parametrize("B", [77, 8192, 9000, 17000])
 def test_phase_engine_ordered_active_list(B, head, monkeypatch):
     """the next trip's active list by order-preserving compaction (phase_compact_kernel) instead of atomic append: the
     same set of trajectories in ascending order, so the same bits; batch sizes below, across and above one pass of
-    the compacting CTA (1024 entries)"""
+    the compacting CTA (8192 entries)"""
     T = 60
     x0, u0 = make_inputs(31337, B, T, 4, 1)
     monkeypatch.setenv("ILQR_B200_HANDOVER", "0")

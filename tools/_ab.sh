@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-tag=ord1
+tag=acc1
 run() { name=$1; cfg=$2; shift; shift
   env "$@" timeout 900 python bench.py --config $cfg --steps 3 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_$name.json 2> gpurun_out/${tag}_$name.err
   python - <<PY
@@ -12,8 +12,8 @@ except Exception as e:
 PY
 }
 for cfg in cfg5 cfg3 cfg4 cfg2; do
-  run ${cfg}_off $cfg
-  run ${cfg}_ordered $cfg ILQR_B200_ORDERED_MIN=0
+  run ${cfg} $cfg
 done
-run cfg2lock_off cfg2 ILQR_B200_HANDOVER=0
-run cfg2lock_ordered cfg2 ILQR_B200_HANDOVER=0 ILQR_B200_ORDERED_MIN=0
+run cfg2lock cfg2 ILQR_B200_HANDOVER=0
+run cfg2_ord cfg2 ILQR_B200_ORDERED_MIN=0
+run cfg4_ord cfg4 ILQR_B200_ORDERED_MIN=0
