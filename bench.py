@@ -408,6 +408,8 @@ def ours_arm(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT, ahead of the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.batch or cfg["B"], cfg["T"]
     n, m = 4, 1
@@ -474,6 +476,7 @@ def ours_arm(args, cfg):
     # whole-job numbers: sum of trips over ranks / max time over ranks
     t_res, cnt = shard.reduce_step_stats([sum(step_ms), sum(e2e_ms), sum(solve_ms), fixed_ms],
                                          [trips, trips_e2e, acc, rej, fixed_trips], dev)
+    per_rank = shard.gather_per_rank([sum(step_ms) / args.steps, sum(e2e_ms) / args.steps, trips / args.steps], dev)
     if rank == 0:
         value = cnt[0] / (t_res[0] * 1e-3)
         e2e = cnt[1] / (t_res[1] * 1e-3)
@@ -540,6 +543,10 @@ def ours_arm(args, cfg):
                          "secondary": secondary},
             "clocks": clocks,
         }
+        if world > 1:  # what the max over ranks is the max OF: every rank solves different instances to termination
+            line["per_rank"] = {"ms_per_step": [round(p[0], 3) for p in per_rank], "e2e_ms_per_step": [round(p[1], 3) for p in per_rank],
+                                "trips_per_step": [int(p[2]) for p in per_rank],
+                                "note": "value = sum of trips / max of ms; a rank's time is set by its own slowest instances"}
         cores = os.cpu_count() or 1
         if world == 1 and not args.no_cpu:
             n_sample = min(B, cores * args.cpu_per_core)

@@ -38,3 +38,13 @@ def reduce_step_stats(elapsed_ms, counts, device):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     return t.tolist(), c.tolist()
+
+
+def gather_per_rank(values, device):
+    """[world][len(values)]: every rank's own numbers (device-timed ms, trip counts), for the bench line's breakdown"""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+    return [t.tolist()]
