@@ -128,8 +128,12 @@ int phase_iterate_t(ilqr_handle *h, int n_iters) {
   }
   long long bound = a.B; /* upper bound of the active count: it never grows */
   /* the head of a trip (sweep + backward) runs one thread per trajectory when the active set can fill the machine that
-   * way, one warp per trajectory below that (ilqr_phases.cuh: phase_pre_warp_kernel) */
-  long long warp_pre_max = 0, rows_max = 24576;
+   * way, 8 lanes per trajectory below that, optionally one warp per trajectory (ilqr_phases.cuh).  The crossover,
+   * measured with ordered active lists (gpurun_out/rm1): closed-form cost derivatives — configs[4] shard 12.59 /
+   * 12.66 / 12.71 / 12.66 M it/s at 6144 / 8192 / 12288 / 24576, configs[1] (4096 trajectories) 3.10 M one thread
+   * each against 3.61 M; finite-difference cost derivatives (each lane also streams its row of C) — configs[3]
+   * (8192 trajectories) 2.55 M it/s at 6144 against 2.46 M at 8192 and above */
+  long long warp_pre_max = 0, rows_max = CD == kCostFD ? 6144 : 12288;
   if (const char *e = getenv("ILQR_B200_WARP_PRE_MAX")) warp_pre_max = atoll(e);
   if (const char *e = getenv("ILQR_B200_ROWS_MAX")) rows_max = atoll(e);
   int rows_gpw = 4;

@@ -68,6 +68,13 @@ ILQR_HD bool lanes_any(unsigned mask, bool p) {
 #endif
 }
 
+#ifndef ILQR_ROLLOUT_PREFETCH
+#define ILQR_ROLLOUT_PREFETCH 4
+#endif
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 /* dst[0..CNT) = src[0..CNT).  `src` points into a dense array of CNT-element runs whose base is 256-byte aligned, so
  * when a run is a multiple of 16 bytes every run is 16-byte aligned and moves as 128-bit accesses. */
 template <int CNT>
@@ -559,6 +566,18 @@ struct Phases {
         load_run<M>(kt_n, tr.k + (size_t)(t + 1) * M);
         load_run<M * N>(Kt_n, tr.K + (size_t)(t + 1) * M * N);
       }
+#if defined(__CUDA_ARCH__) && ILQR_ROLLOUT_PREFETCH > 0
+      /* the nominal arrays of a few steps ahead, into L2: with a full machine the one-step register prefetch above
+       * does not cover a DRAM round trip (ncu, configs[4] shard: 37 % of this kernel's stall samples waited here) */
+      if (t + ILQR_ROLLOUT_PREFETCH < T) {
+        prefetch_l2(tr.xs + (size_t)(t + ILQR_ROLLOUT_PREFETCH) * N);
+        prefetch_l2(tr.K + (size_t)(t + ILQR_ROLLOUT_PREFETCH) * M * N);
+        if ((t & 3) == 0) {
+          prefetch_l2(tr.us + (size_t)(t + ILQR_ROLLOUT_PREFETCH) * M);
+          prefetch_l2(tr.k + (size_t)(t + ILQR_ROLLOUT_PREFETCH) * M);
+        }
+      }
+#endif
       S uc[M];
 #pragma unroll
       for (int j = 0; j < M; j++) {
