@@ -1,6 +1,6 @@
 /*
  * ilqr_phases.cuh — the batch-lockstep engine: one loop trip of src/ilqr_core.cpp:103-288 for EVERY running
- * trajectory of the batch as four kernels, each with the thread mapping that fills its lanes.
+ * trajectory of the batch as five kernels, each with the thread mapping that fills its lanes.
  *
  * The warp-per-trajectory kernel (ilqr_kernel.cuh) gives a trajectory 32 lanes for every phase of a trip, but the
  * phases do not have 32-way work: the line search has n_alpha = 11 rollouts, the backward step (n+m)(n+1) = 25
@@ -10,7 +10,8 @@
  *
  *   sweep     one thread per (trajectory, timestep, variable group): central differences of the Euler step
  *             (src/derivatives.cpp:15-26) and, in FD-cost mode, one cost-stencil output per thread (:29-144);
- *   backward  one thread per trajectory: the whole recursion (:350-401) in registers — Va = [Vxx | Vx], the
+ *   backward  (large active sets; a few thousand run phase_backward_rows_kernel, 8 lanes per trajectory, below)
+ *             one thread per trajectory: the whole recursion (:350-401) in registers — Va = [Vxx | Vx], the
  *             Jacobian of the step, the Q-function — with boxQP (src/boxqp.cpp) inline; 32 trajectories per warp,
  *             every fp64 instruction 32 useful lanes, no shared memory, no barriers.  The next timestep's
  *             Jacobian / state / control are loaded while the current step computes;
@@ -18,8 +19,10 @@
  *             adjacent lanes share the trajectory's nominal arrays (broadcast loads), each streams its candidate
  *             to the trajectory's candidate buffer;
  *   accept    one warp per trajectory: lane 0 applies the reference's serial acceptance order and the lambda
- *             schedule (:199-282), all lanes commit the accepted candidate by a coalesced copy, and trajectories
- *             that go on are appended to the next trip's active list.
+ *             schedule (:199-282), all lanes commit the accepted candidate by a copy of whole timesteps, and the
+ *             trajectories that go on are flagged;
+ *   compact   one CTA: the next trip's active list = the flagged entries of this one, in order (the lists stay
+ *             ascending, so the trajectories of a warp stay neighbours in memory).
  *
  * The batch advances one trip per round of launches; finished trajectories leave the active list, so every launch
  * covers exactly the running ones (ragged trip counts cost nothing but the per-trip latency floor).  Arithmetic is
@@ -30,7 +33,7 @@
  * HBM (per handle, all per TRAJECTORY): F [B][T][n+m][n] Jacobian columns, C [B][T][NCF] (FD-cost mode),
  * cand_x [B][T][n_alpha][n], cand_u [B][T][n_alpha][m] (candidate-interleaved: the n_alpha stores of one timestep are
  * contiguous — with every candidate's block contiguous instead, each store instruction touched eleven DRAM pages and
- * configs[4] lost a quarter of its rate), newcost [B][16], act [2][B] active lists.
+ * configs[4] lost a quarter of its rate), newcost [B][16], act [5][B] active lists and flags (PhaseBufs).
  */
 #ifndef ILQR_PHASES_CUH_
 #define ILQR_PHASES_CUH_
