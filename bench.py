@@ -23,6 +23,9 @@ executed, summed over the batch, per second.
          the same batch; `terminal_cost_vs_gpu` compares the two on that sample, and `like_for_like`
          repeats it with the GPU in the reference's own derivative mode (finite-difference costs) plus
          K, k, cost after 5 trips.
+  e2e_cpp_host  (N = 1) the same batch through the C++ host layer (ilqr_b200/host: BatchSolver, pinned inputs, one
+         ncclAllGather), end to end, as reported by ilqr_b200/host/_build/bench_batch.
+  per_rank  (N > 1) every rank's own ms per step and trips: what the max over ranks is the max of.
   extras  (default line only) short runs of BASELINE configs[2], [3], the configs[4] shard and the opt-in
          FMA build, each with its rate, exit-status histogram and a parity sample against the reference.
 
