@@ -127,21 +127,48 @@ struct Emu : EmuBase {
             for (int t = 0; t < T; t++) Ph::stencil_task(P, xs.data(), us.data(), bufC.data(), o, t);
       }
       Ph::backward_trip(P, tr, bufF.data(), bufC.data(), gterm.data(), st, 1u);
-      const bool reroll = (trip & 1) != 0; /* alternate the two line-search modes: both must give the oracle's bits */
-      if (st.roll == kRollGo)
-        for (int a = 0; a < na; a++)
-          newcost[a] = reroll ? Ph::template rollout_task<Ph::kCostOnly>(P, tr, nullptr, nullptr, a)
-                              : Ph::template rollout_task<Ph::kToCand>(P, tr, candX.data(), candU.data(), a);
-      if (st.status != kRunning) break;
-      const bool fwd = Ph::accept(P, st, newcost);
-      if (fwd) {
-        const int ai = st.alpha_index;
-        if (reroll) {
-          Ph::template rollout_task<Ph::kInPlace>(P, tr, nullptr, nullptr, ai);
-        } else {
-          for (int t = 0; t < T; t++) {
-            for (int c = 0; c < N; c++) xs[(size_t)(t + 1) * N + c] = candX[((size_t)t * na + ai) * N + c];
-            for (int c = 0; c < M; c++) us[(size_t)t * M + c] = candU[((size_t)t * na + ai) * M + c];
+      /* alternate the three line-search modes of the phase kernels: every one must give the oracle's bits */
+      const int mode = trip % 3; /* 0: all candidates kept; 1: cost only + re-roll; 2: staged (ilqr_phases.cuh: PArgs::stage) */
+      const bool reroll = mode == 1;
+      bool fwd = false;
+      if (mode == 2) {
+        const int k = na < 4 ? na : 4; /* kPhaseStageK */
+        if (st.roll == kRollGo)
+          for (int a = 0; a < k; a++) newcost[a] = Ph::template rollout_task<Ph::kToCand>(P, tr, candX.data(), candU.data(), a, k);
+        if (st.status != kRunning) break;
+        TrajState<S> s1 = st; /* stage 1 decides on a copy: nothing is written back unless it accepts or there was no search */
+        const bool f1 = Ph::accept(P, s1, newcost, k);
+        if (f1 || st.roll != kRollGo) {
+          st = s1;
+          fwd = f1;
+          if (fwd) {
+            const int ai = st.alpha_index;
+            for (int t = 0; t < T; t++) {
+              for (int c = 0; c < N; c++) xs[(size_t)(t + 1) * N + c] = candX[((size_t)t * k + ai) * N + c];
+              for (int c = 0; c < M; c++) us[(size_t)t * M + c] = candU[((size_t)t * k + ai) * M + c];
+            }
+          }
+        } else { /* stage 2: the remaining candidates, cost only; an accepted one is re-rolled */
+          for (int a = k; a < na; a++) newcost[a] = Ph::template rollout_task<Ph::kCostOnly>(P, tr, nullptr, nullptr, a);
+          fwd = Ph::accept(P, st, newcost);
+          if (fwd) Ph::template rollout_task<Ph::kInPlace>(P, tr, nullptr, nullptr, st.alpha_index);
+        }
+      } else {
+        if (st.roll == kRollGo)
+          for (int a = 0; a < na; a++)
+            newcost[a] = reroll ? Ph::template rollout_task<Ph::kCostOnly>(P, tr, nullptr, nullptr, a)
+                                : Ph::template rollout_task<Ph::kToCand>(P, tr, candX.data(), candU.data(), a);
+        if (st.status != kRunning) break;
+        fwd = Ph::accept(P, st, newcost);
+        if (fwd) {
+          const int ai = st.alpha_index;
+          if (reroll) {
+            Ph::template rollout_task<Ph::kInPlace>(P, tr, nullptr, nullptr, ai);
+          } else {
+            for (int t = 0; t < T; t++) {
+              for (int c = 0; c < N; c++) xs[(size_t)(t + 1) * N + c] = candX[((size_t)t * na + ai) * N + c];
+              for (int c = 0; c < M; c++) us[(size_t)t * M + c] = candU[((size_t)t * na + ai) * M + c];
+            }
           }
         }
       }

@@ -93,7 +93,10 @@ def test_sixteen_lane_decomposition_equals_oracle_bit_for_bit(golden_solver, cas
     ("integrator_rand_T60_b2", abi.MODEL_DOUBLE_INTEGRATOR, abi.COST_FD, None)])
 def test_phase_engine_source_equals_oracle_bit_for_bit(golden_solver, case, model, cd, kw):
     """the batch-lockstep engine (ilqr_b200/csrc/ilqr_phases.cuh: one thread per sweep task / trajectory / candidate):
-    the functions its kernels call, run task by task on the CPU, reproduce the oracle bit for bit at every trip"""
+    the functions its kernels call, run task by task on the CPU, reproduce the oracle bit for bit at every trip.  The
+    emulation cycles through the three line-search modes of the kernels from trip to trip (tests/emu/ilqr_emu.cpp):
+    every candidate kept, cost-only rollouts + re-roll of the accepted one, and the staged search (first four kept
+    compactly, the rest cost-only where none of those passed)."""
     g = golden_solver
     if kw is None:
         kw = dict(goal=list(g[case + "/goal"]))

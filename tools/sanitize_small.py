@@ -19,6 +19,7 @@ PATHS = [("phase/rows", dict(ILQR_B200_ROWS_MAX="1000000", ILQR_B200_WARP_PRE_MA
          ("phase/warp-head", dict(ILQR_B200_ROWS_MAX="0", ILQR_B200_WARP_PRE_MAX="1000000", ILQR_B200_HANDOVER="0")),
          ("phase/reroll", dict(ILQR_B200_ROWS_MAX="0", ILQR_B200_REROLL_MIN="0", ILQR_B200_HANDOVER="0")),
          ("phase/staged", dict(ILQR_B200_STAGE_MIN="0", ILQR_B200_STAGE_K="2", ILQR_B200_HANDOVER="0")),
+         ("phase/ordered", dict(ILQR_B200_ORDERED_MIN="0", ILQR_B200_HANDOVER="0")),
          ("phase+handover", dict(ILQR_B200_HANDOVER="5", ILQR_B200_CHECK_EVERY="1")),
          ("warp32", dict(ILQR_B200_ENGINE="warp"))]
 if "--lanes16" in sys.argv:
