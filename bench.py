@@ -411,9 +411,9 @@ def ours_arm(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT, ahead of the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        with shard.stdout_to_stderr():  # NCCL prints its version banner on STDOUT, ahead of the one JSON line
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()  # the communicator (and its banner) now, not at the first collective of the run
     B, T = args.batch or cfg["B"], cfg["T"]
     n, m = 4, 1
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2

@@ -2,8 +2,28 @@
 (one process per GPU) owns a contiguous block of the global batch and nothing is exchanged during the
 solve; the ONLY collective is one gather of the final per-instance costs to rank 0 (BASELINE.json north_star,
 SURVEY.md §8e).  Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+import contextlib
+import os
+import sys
+
 import torch
 import torch.distributed as dist
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """Inside the block, file descriptor 1 points at stderr: what native libraries print on STDOUT while a process
+    group comes up (NCCL's "NCCL version ..." banner, printed at NCCL_DEBUG=WARN and VERSION) lands on stderr, so a
+    program whose stdout is a protocol (bench.py: ONE JSON line) keeps it clean.  Restored on exit."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 def shard_bounds(total, world, rank):

@@ -86,3 +86,23 @@ def test_cpp_host_partition_equals_python_partition():
         got = [(int(out[2 * r]), int(out[2 * r + 1])) for r in range(world)]
         assert got == [shard.shard_bounds(total, world, r) for r in range(world)]
         assert got[0][0] == 0 and got[-1][1] == total
+
+
+def test_stdout_to_stderr_redirect(tmp_path):
+    """shard.stdout_to_stderr: what a native library writes to file descriptor 1 inside the block lands on stderr, and
+    stdout is back afterwards (bench.py wraps the NCCL start-up in it: NCCL prints its version banner on stdout)"""
+    import subprocess
+    import sys
+    code = ("import ctypes, os, sys\n"
+            "sys.path.insert(0, %r)\n"
+            "from ilqr_b200 import shard\n"
+            "libc = ctypes.CDLL(None)\n"
+            "print('before', flush=True)\n"
+            "with shard.stdout_to_stderr():\n"
+            "    libc.puts(b'banner from a native library')\n"
+            "    libc.fflush(None)\n"
+            "print('{\"json\": 1}', flush=True)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split("\n")[:2] == ["before", '{"json": 1}']
+    assert "banner from a native library" in out.stderr
