@@ -21,7 +21,9 @@ def _free_port():
 
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    with shard.stdout_to_stderr():  # as bench.py brings its process group up
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dist.barrier()
     try:
         B = 6
         # every rank "solves" its own block: cost of instance b is a function of its GLOBAL index
@@ -29,6 +31,8 @@ def _worker(rank, world, port, out):
         local = torch.arange(lo, hi, dtype=torch.float64) * 1.5 + 0.25
         got = shard.gather_final_costs(local, dst=0)
         t, c = shard.reduce_step_stats([10.0 + rank, 3.0 - rank], [100 + rank, 7], torch.device("cpu"))
+        per = shard.gather_per_rank([50.0 + rank, 1000 + rank], torch.device("cpu"))
+        assert per == [[50.0 + r, 1000.0 + r] for r in range(world)]
         if rank == 0:
             out.put(("costs", got.numpy().tolist()))
             out.put(("stats", t, c))
