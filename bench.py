@@ -537,7 +537,7 @@ def ours_arm(args, cfg):
                     "d2h_bytes_per_step": int(world * (B * sbytes + B * 4))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
-                         "kernel": "one ilqr_solve: the phase kernels (sweep / backward / rollout / accept) of every trip"
+                         "kernel": "one ilqr_solve: the phase kernels (sweep / backward / rollout / accept / compact) of every lockstep trip, then the persistent warp kernel for the survivors"
                                    if engine != "warp" else "ilqr_warp_kernel (op_iterate)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel_ms": solve_s * 1e3,
