@@ -212,7 +212,8 @@ def make_leaf_fixture():
             x0 = rng.normal(size=m) * rng.choice([0.0, 0.3, 3.0])
             res, x, vf, Rf = R.boxqp(Q, c, x0, lo, hi)
             Rpad = np.zeros((3, 3))
-            Rpad[:Rf.shape[0], :Rf.shape[1]] = Rf
+            if res != 6:  # fully clamped (result 6): the reference never factorises and its R is uninitialised memory
+                Rpad[:Rf.shape[0], :Rf.shape[1]] = Rf
             qp.append(dict(m=m, Q=np.pad(Q, ((0, 3 - m), (0, 3 - m))), c=np.pad(c, (0, 3 - m)),
                            x0=np.pad(x0, (0, 3 - m)), lo=np.pad(lo, (0, 3 - m)), hi=np.pad(hi, (0, 3 - m)),
                            result=res, x=np.pad(x, (0, 3 - m)), v_free=np.pad(vf, (0, 3 - m)), R=Rpad,
